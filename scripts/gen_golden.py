@@ -1,0 +1,335 @@
+"""Generate tests/golden/* by EXECUTING THE UNMODIFIED REFERENCE (build container only).
+
+Run:  python scripts/gen_golden.py
+Needs /root/reference (imported via oracle/ref_import.py).  For every case it
+  1. runs the reference function on seeded inputs,
+  2. runs the oracle restatement (oracle/box_oracle.py, oracle/model_oracle.py) on the same inputs
+     and ASSERTS agreement (bit-exact for indices, tight fp32 tolerance for floats) -- this is what
+     pins the oracle, since the reference ships no golden vectors of its own,
+  3. stores inputs + reference outputs as compressed .npz fixtures under tests/golden/.
+The fixtures are what travels to the GPU box; /root/reference does not.
+"""
+import os
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import, box_oracle as bo, model_oracle as mo  # noqa: E402
+
+ref_import.load()
+from nndet.core.boxes import ops as rops                      # noqa: E402
+import importlib                                                # noqa: E402
+rnms = importlib.import_module('nndet.core.boxes.nms')          # noqa: E402
+from nndet.core.boxes.anchors import AnchorGenerator3DS       # noqa: E402
+from nndet.core.boxes.matcher import ATSSMatcher              # noqa: E402
+from nndet.core.boxes.sampler import HardNegativeSamplerBatched  # noqa: E402
+from nndet.core.boxes.coder import BoxCoderND                 # noqa: E402
+from nndet.core.boxes.clip import clip_boxes_to_image_        # noqa: E402
+from nndet.core.retina import BaseRetinaNet                   # noqa: E402
+from nndet.arch.conv import ConvInstanceRelu, ConvGroupRelu, Generator  # noqa: E402
+from nndet.arch.blocks.basic import StackedConvBlock2         # noqa: E402
+from nndet.arch.encoder.modular import Encoder                # noqa: E402
+from nndet.arch.decoder.base import UFPNModular               # noqa: E402
+from nndet.arch.heads.classifier import BCECLassifier         # noqa: E402
+from nndet.arch.heads.regressor import GIoURegressor          # noqa: E402
+from nndet.arch.heads.comb import DetectionHeadHNMNative      # noqa: E402
+from nndet.arch.heads.segmenter import DiCESegmenterFgBg      # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def save(name, **arrs):
+    arrs = {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrs.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print(f"  wrote {name}.npz ({os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.1f} KiB)")
+
+
+def rand_boxes(n, g, extent=160.0, lo=2.0, hi=22.0):
+    """NMS stress boxes: centres U[0,extent)^3, half sizes U[lo,hi)."""
+    c = torch.rand(n, 3, generator=g) * extent
+    h = torch.rand(n, 3, generator=g) * (hi - lo) + lo
+    return torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1],
+                        c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], dim=1)
+
+
+def unique_scores(n, g):
+    return (torch.randperm(n, generator=g).float() + 0.5) / max(n, 1)
+
+
+# ------------------------------------------------------------------------------------------ box metrics
+def gen_pairwise():
+    g = torch.Generator().manual_seed(11)
+    a, b = rand_boxes(37, g), rand_boxes(301, g)
+    b[5] = a[3]                                   # identical pair
+    b[6] = a[3] + 1000.0                          # disjoint
+    iou = rops.box_iou(a, b); giou = rops.generalized_box_iou(a, b, eps=1e-7)
+    dist = rops.box_center_dist(a, b)[0]
+    assert torch.equal(iou, bo.box_iou(a, b)), "oracle box_iou != reference"
+    assert torch.equal(giou, bo.generalized_box_iou(a, b, eps=1e-7)), "oracle giou != reference"
+    assert torch.equal(dist, bo.box_center_dist(a, b)), "oracle center_dist != reference"
+    save("pairwise", a=a, b=b, iou=iou, giou=giou, dist=dist)
+
+
+# ------------------------------------------------------------------------------------------ anchors
+def gen_anchors():
+    for name in ("tiny", "toy", "luna"):
+        arch, anc, patch, _ = mo.make_plan(name)
+        fm = []
+        for lvl in arch["decoder_levels"]:
+            s = [1, 1, 1]
+            for st in arch["strides"][:lvl]:
+                s = [a * b for a, b in zip(s, st)]
+            fm.append([p // q for p, q in zip(patch, s)])
+        gen = AnchorGenerator3DS(**anc)
+        img = torch.zeros(1, 1, *patch)
+        fmaps = [torch.zeros(1, 1, *f) for f in fm]
+        ref = gen(img, fmaps)[0]
+        per_level = gen.get_num_acnhors_per_level()
+        mine, pl = bo.anchors_for_image(patch, fm, anc["width"], anc["height"], anc["depth"])
+        assert torch.equal(ref, mine) and list(per_level) == list(pl), f"anchors differ for {name}"
+        # store a strided sample + checksums (full luna tensor is 24 MB)
+        step = max(1, ref.shape[0] // 4096)
+        save(f"anchors_{name}", patch=patch, fmap_sizes=np.asarray(fm), width=np.asarray(anc["width"]),
+             per_level=np.asarray(per_level), sample_idx=np.arange(0, ref.shape[0], step),
+             sample=ref[::step], colsum=ref.double().sum(0), crc=zlib.crc32(ref.numpy().tobytes()))
+
+
+# ------------------------------------------------------------------------------------------ ATSS
+def gen_atss():
+    arch, anc, patch, _ = mo.make_plan("toy")
+    fm = [[16, 32, 32], [8, 16, 16]]
+    anchors, per_level = bo.anchors_for_image(patch, fm, anc["width"], anc["height"], anc["depth"])
+    matcher = ATSSMatcher(num_candidates=4, similarity_fn=rops.box_iou, center_in_gt=False)
+    cases = {}
+    for seed in range(4):
+        _, tg = mo.synth_batch(patch, 2, 1, 2, 100 + seed, max_gt=6)
+        gt = tg["target_boxes"][0]
+        iou_r, m_r = matcher(gt, anchors, num_anchors_per_level=per_level, num_anchors_per_loc=27)
+        iou_o, m_o = bo.atss_match(gt, anchors, per_level, 27, 4, canonical_ties=True)
+        assert torch.equal(m_r, m_o), f"ATSS matches differ (seed {seed}): {(m_r != m_o).sum()}"
+        assert torch.equal(iou_r, iou_o)
+        cases[f"gt{seed}"] = gt
+        cases[f"pos_idx{seed}"] = torch.where(m_r >= 0)[0]
+        cases[f"pos_gt{seed}"] = m_r[m_r >= 0]
+    # no-GT image
+    _, m_r = matcher(torch.zeros(0, 6), anchors, num_anchors_per_level=per_level, num_anchors_per_loc=27)
+    assert (m_r == -1).all()
+    save("atss_toy", patch=patch, fmap_sizes=np.asarray(fm), per_level=np.asarray(per_level), n_cases=4, **cases)
+
+
+# ------------------------------------------------------------------------------------------ sampler
+def gen_sampler():
+    smp = HardNegativeSamplerBatched(batch_size_per_image=32, positive_fraction=0.33, min_neg=1, pool_size=20)
+    rows = []
+    for npos, nneg, bs in [(0, 1000, 4), (1, 1000, 4), (5, 100000, 4), (500, 4000000, 4), (10, 3, 2), (0, 0, 1),
+                           (41, 50, 4), (43, 5000, 4), (7, 900, 1)]:
+        smp.batch_size_per_image = smp._batch_size_per_image * bs
+        p = smp.get_num_pos(torch.zeros(npos))
+        n = smp.get_num_neg(torch.zeros(nneg), p)
+        pool = min(nneg, int(n * smp.pool_size))
+        assert (p, n, pool) == bo.hnm_counts(npos, nneg, bs), (npos, nneg, bs)
+        rows.append([npos, nneg, bs, p, n, pool])
+    # pool set: reference topk over fg_probs[negative] (tie-free probs)
+    g = torch.Generator().manual_seed(5)
+    A = 50000
+    labels = torch.zeros(A); labels[torch.randperm(A, generator=g)[:60]] = 1.0
+    labels[torch.randperm(A, generator=g)[:500]] = -1.0
+    probs = torch.rand(A, generator=g)
+    negative = torch.where(labels == 0)[0]
+    _, _, pool = bo.hnm_counts(int((labels >= 1).sum()), negative.numel(), 4)
+    ref_pool = torch.sort(negative[probs[negative].topk(pool, sorted=True)[1]])[0]
+    assert torch.equal(ref_pool, bo.hnm_pool(labels, probs, pool))
+    pos, neg, _ = bo.hnm_select(labels, probs, 4, seed=77)
+    save("sampler", counts=np.asarray(rows), labels=labels, probs=probs, pool=ref_pool, pool_size=pool,
+         hash_pos=pos, hash_neg=neg, hash_seed=77)
+
+
+# ------------------------------------------------------------------------------------------ coder / clip
+def gen_coder():
+    g = torch.Generator().manual_seed(3)
+    anchors = rand_boxes(2000, g, extent=128.0)
+    rel = torch.randn(2000, 6, generator=g) * 0.5
+    rel[0, 2] = 10.0                                # exercises the log(1000/16) clamp
+    coder = BoxCoderND(weights=(1.0,) * 6)
+    dec = coder.decode_single(rel, anchors)
+    assert torch.equal(dec, bo.decode_single(rel, anchors)), "decode differs"
+    clipped = clip_boxes_to_image_(dec.clone(), (128, 128, 128))
+    assert torch.equal(clipped, bo.clip_boxes_3d(dec, (128, 128, 128)))
+    keep = rops.remove_small_boxes(clipped, 0.01)
+    assert torch.equal(keep, bo.keep_not_small(clipped, 0.01))
+    save("coder", anchors=anchors, rel=rel, decoded=dec, clipped=clipped, keep=keep)
+
+
+# ------------------------------------------------------------------------------------------ NMS
+def gen_nms():
+    out = {}
+    cases = []
+    for n in (0, 1, 2, 63, 64, 65, 129, 1000, 3000):
+        for thr in (1e-5, 0.1, 0.5, 0.6, 0.9):
+            if n == 3000 and thr not in (0.1, 0.6):
+                continue
+            g = torch.Generator().manual_seed(1000 + n)
+            boxes = rand_boxes(n, g, extent=60.0 if n <= 129 else 160.0)
+            scores = unique_scores(n, g)
+            keep = rnms.nms(boxes, scores, thr) if n > 0 else torch.empty(0, dtype=torch.int64)
+            mine = bo.nms_greedy(boxes, scores, thr, cuda_semantics=True)
+            mine_cpu = bo.nms_greedy(boxes, scores, thr, cuda_semantics=False)
+            assert torch.equal(keep, mine_cpu), f"nms_cpu restatement differs n={n} thr={thr}"
+            assert torch.equal(keep, mine), f"cuda-semantics restatement differs on NaN-free input n={n} thr={thr}"
+            key = f"n{n}_t{thr}"
+            out[key + "_keep"] = keep
+            cases.append((n, thr))
+    # batched (3 classes)
+    g = torch.Generator().manual_seed(4242)
+    boxes = rand_boxes(1500, g); scores = unique_scores(1500, g)
+    idxs = torch.randint(0, 3, (1500,), generator=g)
+    keep = rnms.batched_nms(boxes, scores, idxs, 0.5)
+    assert torch.equal(keep, bo.batched_nms(boxes, scores, idxs, 0.5))
+    out["batched_keep"] = keep
+    save("nms", cases=np.asarray(cases), **out)
+    # NOTE: inputs are regenerated from the seeds by tests (rand_boxes/unique_scores live in tests/util.py too)
+
+
+# ------------------------------------------------------------------------------------------ model
+def det_fill(sd, seed=0):
+    """Deterministic, platform-independent weights keyed by parameter name."""
+    out = {}
+    for k, v in sd.items():
+        rs = np.random.RandomState((zlib.crc32(k.encode()) + seed) & 0x7FFFFFFF)
+        if v.ndim == 0:
+            out[k] = torch.tensor(1.0 + 0.1 * rs.standard_normal(), dtype=v.dtype)
+        elif k.endswith("norm.weight"):
+            out[k] = torch.from_numpy(1.0 + 0.1 * rs.standard_normal(v.shape)).to(v.dtype)
+        elif k.endswith("bias"):
+            out[k] = torch.from_numpy(0.05 * rs.standard_normal(v.shape)).to(v.dtype)
+        else:
+            fan_in = int(np.prod(v.shape[1:])) if v.ndim > 1 else 1
+            out[k] = torch.from_numpy(rs.standard_normal(v.shape) * (1.5 / np.sqrt(fan_in))).to(v.dtype)
+    return out
+
+
+def build_reference_model(arch, anc):
+    """Mirror of RetinaUNetModule.from_config_plan (nndet/ptmodule/retinaunet/base.py:387-466)
+    using the reference's own classes (pytorch_lightning is absent so the LightningModule cannot import)."""
+    conv_b = Generator(ConvInstanceRelu, 3)
+    conv_h = Generator(ConvGroupRelu, 3)
+    enc = Encoder(conv=conv_b, conv_kernels=arch["conv_kernels"], strides=arch["strides"],
+                  block_cls=StackedConvBlock2, in_channels=arch["in_channels"],
+                  start_channels=arch["start_channels"], stage_kwargs=None, max_channels=arch["max_channels"])
+    dec = UFPNModular(conv=conv_b, conv_kernels=arch["conv_kernels"], strides=enc.get_strides(),
+                      in_channels=enc.get_channels(), decoder_levels=arch["decoder_levels"],
+                      fixed_out_channels=arch["fpn_channels"], min_out_channels=8, upsampling_mode="transpose",
+                      num_lateral=1, norm_lateral=False, activation_lateral=False, num_out=1, norm_out=False,
+                      activation_out=False)
+    ag = AnchorGenerator3DS(**anc)
+    apos = ag.num_anchors_per_location()[0]
+    cls = BCECLassifier(conv=conv_h, in_channels=arch["fpn_channels"], internal_channels=arch["head_channels"],
+                        num_classes=arch["classifier_classes"], anchors_per_pos=apos,
+                        num_levels=len(arch["decoder_levels"]), num_convs=1, norm_channels_per_group=16,
+                        norm_affine=True, reduction="mean", loss_weight=1., prior_prob=0.01)
+    reg = GIoURegressor(conv=conv_h, in_channels=arch["fpn_channels"], internal_channels=arch["head_channels"],
+                        anchors_per_pos=apos, num_levels=len(arch["decoder_levels"]), num_convs=1,
+                        norm_channels_per_group=16, norm_affine=True, reduction="sum", loss_weight=1.,
+                        learn_scale=True)
+    sampler = HardNegativeSamplerBatched(batch_size_per_image=32, positive_fraction=0.33, pool_size=20, min_neg=1)
+    head = DetectionHeadHNMNative(classifier=cls, regressor=reg, coder=BoxCoderND(weights=(1.0,) * 6),
+                                  sampler=sampler, log_num_anchors=None)
+    seg = DiCESegmenterFgBg(conv_b, seg_classes=arch["seg_classes"], in_channels=dec.get_channels(),
+                            decoder_levels=arch["decoder_levels"], dice_kwargs={"batch_dice": True})
+    matcher = ATSSMatcher(similarity_fn=rops.box_iou, num_candidates=4, center_in_gt=False)
+    return BaseRetinaNet(dim=3, encoder=enc, decoder=dec, head=head, anchor_generator=ag, matcher=matcher,
+                         num_classes=arch["classifier_classes"], decoder_levels=arch["decoder_levels"],
+                         segmenter=seg, detections_per_img=100, score_thresh=0, topk_candidates=10000,
+                         remove_small_boxes=0.01, nms_thresh=0.6)
+
+
+class _HashSamplerMixin:
+    """Test double for the RNG only: replaces torch.randperm draws (sampler.py:93,205) with the
+    counter-hash priorities of oracle.box_oracle so reference and CUDA path pick the same anchors."""
+    seed = 0
+
+    def select_positives(self, positive, num_pos, img_labels, img_fg_probs):
+        pr = bo.hash_priority(positive.numpy(), self.seed, 1).astype(np.uint64) * (1 << 32) + positive.numpy().astype(np.uint64)
+        sel = positive[torch.from_numpy(np.argsort(pr, kind="stable")[:num_pos])]
+        m = torch.zeros_like(img_labels, dtype=torch.uint8); m[sel] = 1
+        return m
+
+    def select_negatives(self, negative, num_neg, img_labels, img_fg_probs):
+        pool = min(negative.numel(), int(num_neg * self.pool_size))
+        _, ip = img_fg_probs[negative].topk(pool, sorted=True)
+        negative = torch.sort(negative[ip])[0]
+        pr = bo.hash_priority(negative.numpy(), self.seed, 2).astype(np.uint64) * (1 << 32) + negative.numpy().astype(np.uint64)
+        sel = negative[torch.from_numpy(np.argsort(pr, kind="stable")[:num_neg])]
+        m = torch.zeros_like(img_labels, dtype=torch.uint8); m[sel] = 1
+        return m
+
+
+class HashSampler(_HashSamplerMixin, HardNegativeSamplerBatched):
+    pass
+
+
+def gen_model(name="tiny", seed=0):
+    arch, anc, patch, bs = mo.make_plan(name)
+    torch.manual_seed(0)
+    ref = build_reference_model(dict(arch), dict(anc))
+    orc = mo.RetinaUNetOracle(dict(arch), dict(anc))
+    rk, ok = list(ref.state_dict().keys()), list(orc.state_dict().keys())
+    assert sorted(rk) == sorted(ok), f"state_dict keys differ:\n{set(rk) ^ set(ok)}"
+    for k in rk:
+        assert ref.state_dict()[k].shape == orc.state_dict()[k].shape, k
+    sd = det_fill(ref.state_dict(), seed)
+    ref.load_state_dict(sd); orc.load_state_dict(sd)
+    hs = HashSampler(batch_size_per_image=32, positive_fraction=0.33, pool_size=20, min_neg=1)
+    hs.seed = 123
+    ref.head.fg_bg_sampler = hs
+
+    images, targets = mo.synth_batch(patch, bs, arch["in_channels"], arch["classifier_classes"], 2024 + seed)
+    t_ref = {k: ([x.clone() for x in v] if isinstance(v, list) else v.clone()) for k, v in targets.items()}
+    ref.train(); orc.train()
+    losses_r, pred_r = ref.train_step(images, t_ref, evaluation=True, batch_num=0)
+    sum(losses_r.values()).backward()
+    losses_o, aux = orc.train_step(images, targets, seed=123)
+    sum(losses_o.values()).backward()
+    for k in losses_r:
+        assert torch.allclose(losses_r[k], losses_o[k], rtol=1e-5, atol=1e-6), (k, losses_r[k], losses_o[k])
+    gr = {k: p.grad for k, p in ref.named_parameters()}
+    go = {k: p.grad for k, p in orc.named_parameters()}
+    for k in gr:
+        assert torch.allclose(gr[k], go[k], rtol=1e-3, atol=1e-5), f"grad {k}: {(gr[k] - go[k]).abs().max()}"
+    post_o = orc.postprocess(images, {k: v.detach() for k, v in aux["pred"].items()}, aux["anchors"])
+    for i in range(bs):
+        assert torch.equal(pred_r["pred_labels"][i], post_o[i][2]), "postprocess labels differ"
+        assert torch.allclose(pred_r["pred_boxes"][i], post_o[i][0], atol=1e-4), "postprocess boxes differ"
+        assert torch.allclose(pred_r["pred_scores"][i], post_o[i][1], atol=1e-6)
+
+    with torch.no_grad():
+        pd, _, ps = ref(images)
+    arrs = dict(seed=seed, sampler_seed=123, images_crc=zlib.crc32(images.numpy().tobytes()),
+                box_logits=pd["box_logits"], box_deltas=pd["box_deltas"][::7],
+                seg_logits=ps["seg_logits"][:, :, ::2, ::2, ::2],
+                pos_idx=aux["pos"], neg_idx=aux["neg"], labels_nonzero_idx=torch.where(aux["labels"] != 0)[0],
+                labels_nonzero=aux["labels"][aux["labels"] != 0])
+    for k, v in losses_r.items():
+        arrs["loss_" + k] = v.detach()
+    for k, gv in gr.items():
+        arrs["gnorm/" + k] = gv.double().norm()
+        arrs["ghead/" + k] = gv.reshape(-1)[:16]
+    for i in range(bs):
+        arrs[f"det_boxes{i}"] = pred_r["pred_boxes"][i]
+        arrs[f"det_scores{i}"] = pred_r["pred_scores"][i]
+        arrs[f"det_labels{i}"] = pred_r["pred_labels"][i]
+    save(f"model_{name}", **arrs)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "model"]
+    for w in which:
+        print("==", w)
+        globals()["gen_" + w]()
+    print("all reference/oracle agreement assertions passed")
