@@ -1,0 +1,80 @@
+"""GPU parity: nndetection_b200._C.nms (C ABI: nnd_nms3d_f32) vs the oracle and the reference's golden keep lists."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_oracle as bo
+import tutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _nms(boxes, scores, thr):
+    from nndetection_b200 import _C
+    return _C.nms(boxes.cuda(), scores.cuda(), thr).cpu()
+
+
+def test_golden_keep_lists_bit_exact():
+    g = util.golden("nms")
+    for n, thr in g["cases"].tolist():
+        n = int(n)
+        boxes, scores = util.nms_case(n)
+        keep = _nms(boxes, scores, thr)
+        assert keep.dtype == torch.int64
+        assert torch.equal(keep, torch.from_numpy(g[f"n{n}_t{thr}_keep"])), (n, thr)
+
+
+@pytest.mark.parametrize("n,thr", [(10000, 0.1), (10000, 0.6), (20000, 0.5)])
+def test_vs_oracle_large(n, thr):
+    boxes, scores = util.nms_case(n)
+    assert torch.equal(_nms(boxes, scores, thr), bo.nms_greedy(boxes, scores, thr))
+
+
+def test_batched_golden():
+    from nndetection_b200.core.boxes.nms import batched_nms
+    g = util.golden("nms")
+    gen = torch.Generator().manual_seed(4242)
+    boxes = util.rand_boxes(1500, gen); scores = util.unique_scores(1500, gen)
+    idxs = torch.randint(0, 3, (1500,), generator=gen)
+    keep = batched_nms(boxes.cuda(), scores.cuda(), idxs.cuda(), 0.5).cpu()
+    assert torch.equal(keep, torch.from_numpy(g["batched_keep"]))
+
+
+def test_edge_cases():
+    from nndetection_b200 import _C
+    e = _C.nms(torch.zeros(0, 6).cuda(), torch.zeros(0).cuda(), 0.5)
+    assert e.shape == (0,) and e.dtype == torch.int64 and e.is_cuda
+    with pytest.raises(RuntimeError):
+        _C.nms(torch.zeros(3, 6), torch.zeros(3), 0.5)
+    # zero-volume duplicates: NaN IoU never suppresses (CUDA semantics of the reference kernel)
+    b = torch.tensor([[1., 1, 1, 1, 1, 1], [1., 1, 1, 1, 1, 1], [0., 0, 2, 2, 0, 2]])
+    s = torch.tensor([0.9, 0.8, 0.7])
+    assert _nms(b, s, 0.5).tolist() == [0, 1, 2]
+    # equal scores: stable order (ascending index)
+    b = util.rand_boxes(500, torch.Generator().manual_seed(1))
+    s = torch.full((500,), 0.5)
+    assert torch.equal(_nms(b, s, 0.3), bo.nms_greedy(b, s, 0.3))
+    # negative threshold: every later box with non-NaN IoU is suppressed
+    assert _nms(b, util.unique_scores(500, torch.Generator().manual_seed(2)), -1.0).numel() == 1
+    # 2-D boxes
+    b2 = b[:, :4].contiguous()
+    s2 = util.unique_scores(500, torch.Generator().manual_seed(3))
+    import torchvision
+    assert torch.equal(_nms(b2, s2, 0.4), torchvision.ops.nms(b2, s2, 0.4))
+
+
+def test_idempotent_and_sorted_property_100k():
+    # size-independent properties at BASELINE config 4's N: keep is score-sorted, NMS(keep) == keep
+    n = 100_000
+    g = torch.Generator().manual_seed(9)
+    boxes, scores = util.rand_boxes(n, g), util.unique_scores(n, g)
+    keep = _nms(boxes, scores, 0.1)
+    ks = scores[keep]
+    assert (ks[:-1] > ks[1:]).all()
+    keep2 = _nms(boxes[keep], ks, 0.1)
+    assert torch.equal(keep2, torch.arange(keep.numel()))
+    # pairwise IoU among the kept set never exceeds the threshold (checked on a slice)
+    sub = boxes[keep[:3000]]
+    iou = bo.box_iou(sub, sub)
+    iou.fill_diagonal_(0)
+    assert float(iou.max()) <= 0.1

@@ -1,0 +1,46 @@
+"""Seeded synthetic inputs shared by CPU and GPU tests (identical to scripts/gen_golden.py generators)."""
+import os
+import zlib
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def rand_boxes(n, g, extent=160.0, lo=2.0, hi=22.0):
+    c = torch.rand(n, 3, generator=g) * extent
+    h = torch.rand(n, 3, generator=g) * (hi - lo) + lo
+    return torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1],
+                        c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], dim=1)
+
+
+def unique_scores(n, g):
+    return (torch.randperm(n, generator=g).float() + 0.5) / max(n, 1)
+
+
+def nms_case(n, extent=None):
+    g = torch.Generator().manual_seed(1000 + n)
+    boxes = rand_boxes(n, g, extent=(60.0 if n <= 129 else 160.0) if extent is None else extent)
+    return boxes, unique_scores(n, g)
+
+
+def det_fill(sd, seed=0):
+    """Deterministic, platform-independent weights keyed by parameter name (same as scripts/gen_golden.py)."""
+    out = {}
+    for k, v in sd.items():
+        rs = np.random.RandomState((zlib.crc32(k.encode()) + seed) & 0x7FFFFFFF)
+        if v.ndim == 0:
+            out[k] = torch.tensor(1.0 + 0.1 * rs.standard_normal(), dtype=v.dtype)
+        elif k.endswith("norm.weight"):
+            out[k] = torch.from_numpy(1.0 + 0.1 * rs.standard_normal(v.shape)).to(v.dtype)
+        elif k.endswith("bias"):
+            out[k] = torch.from_numpy(0.05 * rs.standard_normal(v.shape)).to(v.dtype)
+        else:
+            fan_in = int(np.prod(v.shape[1:])) if v.ndim > 1 else 1
+            out[k] = torch.from_numpy(rs.standard_normal(v.shape) * (1.5 / np.sqrt(fan_in))).to(v.dtype)
+    return out
