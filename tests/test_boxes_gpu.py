@@ -42,7 +42,7 @@ def test_pairwise_metrics(E):
     g = util.golden("pairwise")
     a, b = T(g["a"]).cuda(), T(g["b"]).cuda()
     assert torch.equal(E.pairwise(a, b, 0).cpu(), T(g["iou"]))       # same fp32 op sequence -> bit-exact
-    assert torch.equal(E.pairwise(a, b, 2).cpu(), T(g["dist"]))
+    torch.testing.assert_close(E.pairwise(a, b, 2).cpu(), T(g["dist"]), rtol=1e-6, atol=1e-6)   # sum order of 3 squares
     torch.testing.assert_close(E.pairwise(a, b, 1, 1e-7).cpu(), T(g["giou"]), rtol=1e-6, atol=1e-7)
 
 
@@ -143,10 +143,13 @@ def test_sampler_golden_and_edge_cases(E):
     assert torch.equal(torch.sort(pool[:c[4]].cpu().long())[0], torch.arange(c[4]))
     # fewer negatives than the pool
     lab = torch.full((500,), -1.0); lab[:7] = 0; lab[100:103] = 2
-    counts, pos, neg, pool, _ws = E.hnm_sample(lab.cuda(), torch.rand(500).cuda(), plan, seed=1, want_pool=True)
+    pr = torch.rand(500)
+    counts, pos, neg, pool, _ws = E.hnm_sample(lab.cuda(), pr.cuda(), plan, seed=1, want_pool=True)
     c = counts.cpu().tolist()
     assert (c[0], c[1], c[2], c[3], c[4]) == (3, 7) + bo.hnm_counts(3, 7, 4)
-    assert pos[:3].cpu().tolist() == [100, 101, 102] and neg[:c[3]].cpu().tolist() == list(range(7))
+    pos_o, neg_o, pool_o = bo.hnm_select(lab, pr, 4, 1)
+    assert pos[:3].cpu().tolist() == [100, 101, 102] and torch.equal(neg[:c[3]].cpu(), neg_o)
+    assert torch.sort(pool[:c[4]].cpu().long())[0].tolist() == list(range(7))
 
 
 def test_postprocess_vs_oracle(E):
