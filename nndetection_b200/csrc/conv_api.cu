@@ -1,0 +1,75 @@
+// C-ABI entry points of the convolution family (include/nndet_b200.h).  Geometry travels as a flat int array:
+//   geom[0..20] = N, Di, Hi, Wi, Cin,  Ld, Lh, Lw,  sd, sh, sw,  Do, Ho, Wo,  omd, omh, omw,  ood, ooh, oow,  T
+//   geom[21 + 4*t ..] = off_d, off_h, off_w, weight_tap   for each of the T taps
+// (see conv_common.cuh for the gather-convolution form these numbers describe).
+#include "conv_common.cuh"
+
+int nnd_conv_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_wgrad(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                   long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_first_fprop(const float* x, const float* w, const ConvGeom& g, int Cout, __nv_bfloat16* out, float* stat_sum,
+                         float* stat_sq, cudaStream_t st);
+int nnd_conv_first_wgrad(const float* x, const __nv_bfloat16* dy, const ConvGeom& g, int Cout, float* dw, cudaStream_t st);
+
+namespace {
+int parse_geom(const int* a, ConvGeom& g) {
+  if (!a) return NND_ERR_ARG;
+  g.N = a[0]; g.Di = a[1]; g.Hi = a[2]; g.Wi = a[3]; g.Cin = a[4];
+  g.Ld = a[5]; g.Lh = a[6]; g.Lw = a[7];
+  g.sd = a[8]; g.sh = a[9]; g.sw = a[10];
+  g.Do = a[11]; g.Ho = a[12]; g.Wo = a[13];
+  g.omd = a[14]; g.omh = a[15]; g.omw = a[16]; g.ood = a[17]; g.ooh = a[18]; g.oow = a[19];
+  g.T = a[20];
+  if (g.T < 1 || g.T > NND_MAX_TAPS) return NND_ERR_ARG;
+  for (int t = 0; t < g.T; ++t) {
+    g.off_d[t] = (signed char)a[21 + 4 * t]; g.off_h[t] = (signed char)a[22 + 4 * t]; g.off_w[t] = (signed char)a[23 + 4 * t];
+    g.tap_w[t] = (unsigned char)a[24 + 4 * t];
+  }
+  return NND_OK;
+}
+int g_force_igemm = 0;
+}  // namespace
+
+extern "C" {
+
+// 1: route eligible layers to the tcgen05 kernel (default), 0: always use the mma.sync kernel (cross-check / debugging)
+void nnd_conv_set_tensor_path(int enable_tcgen05) { g_force_igemm = !enable_tcgen05; }
+
+int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
+                         long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
+                         const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  ConvEpilogue ep;
+  ep.out = out; ep.out_n_stride = out_n_stride; ep.out_v_stride = out_v_stride; ep.out_fp32 = out_fp32;
+  ep.Cout = Cout; ep.CoutPad = CoutPad; ep.bias = bias; ep.scale = scale;
+  ep.residual = (const __nv_bfloat16*)residual; ep.stat_sum = stat_sum; ep.stat_sq = stat_sq;
+  const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
+  if (used_tc) *used_tc = tc ? 1 : 0;
+  if (tc) return nnd_conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+  return nnd_conv_igemm((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+}
+
+int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom, float* dw, long long s_co,
+                        long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  return nnd_conv_wgrad((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
+}
+
+int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom, int Cout, void* out, float* stat_sum,
+                             float* stat_sq, cudaStream_t st) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  return nnd_conv_first_fprop(x, w, g, Cout, (__nv_bfloat16*)out, stat_sum, stat_sq, st);
+}
+
+int nnd_conv_first_wgrad_f32(const float* x, const void* dy, const int* geom, int Cout, float* dw, cudaStream_t st) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  return nnd_conv_first_wgrad(x, (const __nv_bfloat16*)dy, g, Cout, dw, st);
+}
+
+}  // extern "C"
