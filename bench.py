@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: full Retina U-Net train step (forward + losses + detection post-processing with 3-D NMS
++ backward + gradient all-reduce + SGD) on synthetic LUNA16-shaped patches (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "patches/sec (128^3 1ch) full train step + 3D NMS"
+UNIT = "patches/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def conv_flops_per_patch(arch, patch):
+    """Closed-form forward conv FLOPs (2 * Cin * Cout * k^3 * output voxels), SURVEY 8d."""
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    import numpy as np
+    fl = 0
+    sp = list(patch)
+    chans, sps = [], []
+    c = arch["in_channels"]
+    for i, k in enumerate(arch["conv_kernels"]):
+        co = arch["start_channels"] if i == 0 else min(c * 2, arch.get("max_channels", 320))
+        if i > 0:
+            sp = [a // b for a, b in zip(sp, arch["strides"][i - 1])]
+        v = sp[0] * sp[1] * sp[2]
+        kk = int(np.prod(k))
+        fl += 2 * c * co * kk * v + 2 * co * co * kk * v
+        c = co
+        chans.append(co); sps.append(list(sp))
+    n = len(chans)
+    oc = [arch["fpn_channels"]] * n
+    for ol in [l for l in range(n) if l < min(arch["decoder_levels"])][::-1]:
+        oc[ol] = max(8, oc[ol + 1] // 2)
+    for l in range(n):
+        v = sps[l][0] * sps[l][1] * sps[l][2]
+        fl += 2 * chans[l] * oc[l] * v + 2 * oc[l] * oc[l] * int(np.prod(arch["conv_kernels"][l])) * v
+        if l > 0:
+            fl += 2 * oc[l] * oc[l - 1] * int(np.prod(arch["strides"][l - 1])) * v
+    hc, C = arch["head_channels"], arch["classifier_classes"]
+    for l in arch["decoder_levels"]:
+        v = sps[l][0] * sps[l][1] * sps[l][2]
+        fl += 2 * (2 * 27 * (oc[l] * hc + hc * hc) * v)            # c_in + c_internal0, classifier and regressor
+        fl += 2 * 27 * hc * (27 * C + 162) * v
+    fl += 2 * oc[0] * 2 * sps[0][0] * sps[0][1] * sps[0][2]
+    return fl
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port: identical torch-CPU operators), all host
+    threads; each step = ONE 128^3 patch (bounded sample of the batch-4 workload) train step + post-processing."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import model_oracle as mo
+    torch.set_num_threads(os.cpu_count())
+    arch, anc, patch, bs = mo.make_plan("luna")
+    net = mo.RetinaUNetOracle(dict(arch), dict(anc))
+    images, targets = mo.synth_batch(patch, 1, arch["in_channels"], arch["classifier_classes"], 1234)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=3e-5)
+
+    def step():
+        opt.zero_grad()
+        losses, aux = net.train_step(images, targets, seed=1)
+        net.postprocess(images, {k: v.detach() for k, v in aux["pred"].items()}, aux["anchors"])
+        sum(losses.values()).backward()
+        opt.step()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = args.steps * 1 / dt
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "luna16 128^3 1ch (reference CPU path, 1 patch per step)", "batch_per_step": 1},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"{args.steps} train steps of 1 patch (fwd+loss+postprocess/nms_cpu+bwd+SGD), torch CPU fp32"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="luna")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        args.steps = min(args.steps, 5)
+        return run_reference(args)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nndetection_b200 import _lib as L
+    from nndetection_b200.configs import make_plan, synth_batch
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    from nndetection_b200.training import Trainer
+    from nndetection_b200.arch import conv_ops
+
+    lib = L.lib()                       # raises if the CUDA extension is missing: no fallback
+    lib.nnd_launch_count.restype = __import__("ctypes").c_ulonglong
+    if args.igemm_only:
+        conv_ops.set_tensor_path(False)
+    arch, anc, patch, bs = make_plan(args.config)
+    torch.manual_seed(1234 + rank)
+    net = RetinaUNetV001.from_config_plan(None, arch, anc).to(dev)
+    trainer = Trainer(net, distributed=world > 1)
+
+    # ---- synthetic data: 4 distinct batches (> L2: one batch of activations alone is GBs), pinned on the host
+    n_batches = 4
+    host = []
+    for i in range(n_batches):
+        im, tg = synth_batch(patch, bs, arch["in_channels"], arch["classifier_classes"], 1234 + 97 * rank + i)
+        host.append((im.pin_memory(), [b.pin_memory() for b in tg["target_boxes"]], [c.pin_memory() for c in tg["target_classes"]],
+                     tg["target_seg"].pin_memory()))
+    resident = [(im.to(dev), {"target_boxes": [b.to(dev) for b in tb], "target_classes": [c.to(dev) for c in tc],
+                              "target_seg": sg.to(dev)}) for im, tb, tc, sg in host]
+    h2d_bytes = host[0][0].numel() * 4 + host[0][3].numel() * 4 + sum(b.numel() * 4 for b in host[0][1]) + sum(c.numel() * 8 for c in host[0][2])
+
+    def step_resident(i):
+        im, tg = resident[i % n_batches]
+        return trainer.train_step(im, tg, evaluation=True)
+
+    def step_e2e(i):
+        im, tb, tc, sg = host[i % n_batches]
+        imd = im.to(dev, non_blocking=True)
+        tg = {"target_boxes": [b.to(dev, non_blocking=True) for b in tb], "target_classes": [c.to(dev, non_blocking=True) for c in tc],
+              "target_seg": sg.to(dev, non_blocking=True)}
+        losses, pred = trainer.train_step(imd, tg, evaluation=True)
+        vals = torch.stack([losses[k].detach().float() for k in ("reg", "cls", "seg_ce", "seg_dice")]).cpu()   # D2H result read
+        nb = sum(int(b.shape[0]) for b in pred["pred_boxes"])
+        return vals, nb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.nnd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.nnd_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    d2h = 0
+    for i in range(args.steps):
+        vals, nb = step_e2e(i)
+        d2h = 16 + 4 * bs + nb * (24 + 4 + 8)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel family (gather convolution), measured live with CUDA events
+    roof = None
+    if rank == 0:
+        roof = conv_roofline(net, dev, arch, patch, bs)
+
+    if rank == 0:
+        value = world * bs * args.steps / (ms / 1e3)
+        e2e_v = world * bs * args.steps / (ms_e2e / 1e3)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"{args.config}: {patch[0]}x{patch[1]}x{patch[2]} {arch['in_channels']}ch, batch {bs}/GPU, "
+                                      f"full train step (fwd+ATSS+HNM+losses+postprocess/3D-NMS+bwd+SGD)",
+                          "global_batch": bs * world, "parallelism": f"dp{world}",
+                          "l2": f"{n_batches} distinct input batches; per-step activations (> 4 GB) exceed the 126 MB L2"},
+               "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+               "train_tflops": 3 * conv_flops_per_patch(arch, patch) * bs * world * args.steps / (ms / 1e3) / 1e12}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(net, dev, arch, patch, bs):
+    """Dominant kernel = the gather convolution of the largest layer (encoder stage 0, conv 2: 32->32 at full
+    resolution, 464 GFLOP per batch-4 launch = 16.8 % of the forward FLOPs).  achieved = algorithmic FLOPs / mean
+    launch time over 5 launches (CUDA events on the launch stream, after 2 warm-ups)."""
+    from nndetection_b200.arch import conv_ops as ops
+    hbm, tf_burst, tf_sus, kind = peaks()
+    layer = net.encoder.stages[0].convs[0][1]
+    cin, cout = layer.conv.in_channels, layer.conv.out_channels
+    x = torch.randn(bs, cin, *patch, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    plan = layer.plan(bs, tuple(patch))
+    wp, _ = layer.packed()
+    y = ops.empty_cl(bs, cout, plan.out_sp, device=dev)
+    st = torch.zeros((2, bs, cout), dtype=torch.float32, device=dev)
+    used = 0
+    for _ in range(2):
+        used = ops.conv_gather(x, wp, plan.fprop[0], y, cout, cout, stat_sum=st[0], stat_sq=st[1])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 5
+    e0.record()
+    for _ in range(n):
+        ops.conv_gather(x, wp, plan.fprop[0], y, cout, cout, stat_sum=st[0], stat_sq=st[1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    vox = bs * patch[0] * patch[1] * patch[2]
+    flops = 2.0 * 27 * cin * cout * vox
+    achieved = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_tc (tcgen05)" if used else "conv_igemm_kernel<32> (mma.sync)",
+            "layer": f"encoder.stage0.conv2 {cin}->{cout} 3x3x3 @ {patch[0]}^3 x batch {bs}",
+            "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst, "peak_kind": kind + " burst bf16 cuBLAS",
+            "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": None}
+
+
+def cpu_baseline():
+    """Oracle port (the reference's torch-CPU operators) on the host cores: ONE train step of ONE 128^3 patch."""
+    from oracle import model_oracle as mo
+    torch.set_num_threads(os.cpu_count())
+    arch, anc, patch, bs = mo.make_plan("luna")
+    net = mo.RetinaUNetOracle(dict(arch), dict(anc))
+    images, targets = mo.synth_batch(patch, 1, arch["in_channels"], arch["classifier_classes"], 1234)
+    t0 = time.perf_counter()
+    losses, aux = net.train_step(images, targets, seed=1)
+    net.postprocess(images, {k: v.detach() for k, v in aux["pred"].items()}, aux["anchors"])
+    sum(losses.values()).backward()
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 train step of 1 patch (fwd+loss+postprocess+bwd), torch CPU fp32, un-warmed"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/* nndet_b200.h -- C ABI of libnndet_b200.so: the B200 (sm_100a) hot path of nnDetection.
+ *
+ * Every entry point: plain pointers + sizes, explicit cudaStream_t, caller-provided workspace (so it can come from
+ * the host framework's allocator), returns an int status (0 ok / 1 bad argument / 2 workspace too small / 3 CUDA
+ * error -> nnd_last_error()), never throws, never synchronises with the host.  All pointers are DEVICE pointers
+ * unless named *_host.  Reference citations are file:line under MIC-DKFZ/nnDetection.
+ *
+ * The reference's only native interface on this path is the pybind symbol
+ *     nndet._C.nms(dets, scores, iou_threshold) -> int64 indices      (nndet/csrc/ops.cpp:13-15)
+ * which nnd_nms3d_f32 / nnd_nms2d_f32 replace; the other families replace the torch/ATen/cuDNN calls the
+ * reference's Python issues for the same step (cited per function).  INTEGRATION.md shows the bindings.
+ */
+#ifndef NNDET_B200_H
+#define NNDET_B200_H
+#include <stddef.h>
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NND_OK 0
+#define NND_ERR_ARG 1
+#define NND_ERR_WORKSPACE 2
+#define NND_ERR_CUDA 3
+
+int nnd_abi_version(void);
+const char* nnd_last_error(void);              /* text of the last NND_ERR_CUDA on this thread */
+const char* nnd_build_arch(void);              /* "sm_100a" */
+unsigned long long nnd_launch_count(void);     /* kernels launched through this library so far */
+
+/* ---- 3-D / 2-D greedy NMS.  Replaces nms_cuda + nms_kernel(_3d) + devIoU(_3d), nndet/csrc/cuda/nms.cu:148-221,54-145,22-51,
+ *      and the dispatch in nndet/csrc/cpu/nms.cpp:18-34.  boxes [n, 6|4] (x1,y1,x2,y2[,z1,z2]) fp32, scores [n] fp32.
+ *      keep_out [n] int64: indices into `boxes` by descending score; n_keep_out: device scalar. */
+size_t nnd_nms_workspace_bytes(long long n, int dim /* 2 or 3 */);
+int nnd_nms3d_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long* keep_out,
+                  long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+int nnd_nms2d_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long* keep_out,
+                  long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- anchors: one pyramid level of AnchorGenerator3D.grid_anchors, nndet/core/boxes/anchors.py:337-377.
+ *      out [s0*s1*s2*nb, 6]; base [nb, 6] (generate_anchors, anchors.py:526-549); size3/stride3 host ints. */
+int nnd_anchor_grid_f32(float* out, const float* base, int nb, const int* size3_host, const int* stride3_host, cudaStream_t stream);
+
+/* ---- pairwise metrics [n, m]: mode 0 box_iou (nndet/core/boxes/ops.py:131-159), 1 generalized_box_iou (ops.py:162-185),
+ *      2 box_center_dist (ops.py:262-287). */
+int nnd_box_pairwise_f32(const float* b1, const float* b2, int n, int m, float eps, int mode, float* out, cudaStream_t stream);
+
+/* ---- decode_single (nndet/core/boxes/coder.py:90-155, weights 1) [+ clip_boxes_to_image_3d_ (clip.py:83-101)].
+ *      deltas/out [n, 6]; anchors [A, 6] reused cyclically (n = batch * A); clip_shape3_host NULL = no clip. */
+int nnd_decode_boxes_f32(const float* deltas, const float* anchors, long long n, long long A, float xform_clip,
+                         const float* clip_shape3_host, float* out, cudaStream_t stream);
+/* ---- sigmoid of logits [n, C] -> probs_out [n, C] (optional) and max over classes fg_out [n] (optional); comb.py:262-263 */
+int nnd_sigmoid_fg_f32(const float* logits, long long n, int C, float* probs_out, float* fg_out, cudaStream_t stream);
+
+/* ---- ATSS matching of a whole batch.  Replaces ATSSMatcher.compute_matches (nndet/core/boxes/matcher/atss.py:48-122) and the
+ *      per-image loop of assign_targets_to_anchors (nndet/core/retina.py:256-262).  gt [G, 6] (all images), gt_img[g] image of
+ *      box g, gt_local[g] its index inside that image; anchors [A, 6]; level_off [L+1] anchor offsets of the pyramid levels
+ *      (device + host copy); kc = num_candidates * anchors_per_location; matches_out [B*A] int64 (-1 = background). */
+size_t nnd_atss_workspace_bytes(int G, int A, const int* level_off_host, int L, int kc);
+int nnd_atss_match(const float* gt, const int* gt_img, const int* gt_local, int G, const float* anchors, int A, int B,
+                   const int* level_off_dev, const int* level_off_host, int L, int kc, long long* matches_out, void* ws,
+                   size_t ws_bytes, cudaStream_t stream);
+/* labels [n] fp32: 0 background, class+1 foreground, -1 ignore (retina.py:263-288); gt_off[b] first gt of image b */
+int nnd_assign_labels(const long long* matches, long long n, long long A, const long long* gt_classes, const int* gt_off,
+                      float* labels_out, cudaStream_t stream);
+
+/* ---- hard-negative sampler.  Replaces HardNegativeSamplerBatched.__call__ (nndet/core/boxes/sampler.py:212-270).
+ *      counts_out int32[8]: #positive, #negative, num_pos, num_neg, pool, pool filled, pos-list overflow, -.
+ *      pos_out / neg_out: ascending anchor indices (int64); *pool_list_out points into ws (int32[pool], unordered). */
+int nnd_hnm_max_select(void);
+size_t nnd_hnm_workspace_bytes(long long n, int pos_cap, int pool_cap);
+int nnd_hnm_sample(const float* labels, const float* fg_probs, long long n, int max_pos, double neg_ratio, int min_neg,
+                   double pool_size, unsigned int seed, int* counts_out, long long* pos_out, long long* neg_out, int pos_cap,
+                   int pool_cap, int** pool_list_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+/* ---- head losses.  Replaces DetectionHeadHNMNative.compute_loss (nndet/arch/heads/comb.py:383-405): decode sampled positives,
+ *      GIoU loss (nndet/losses/regression.py:118-162) / max(1, P), BCE-with-logits one-hot mean (classification.py:137-181).
+ *      losses_out[2] = {reg, cls}; compact gradients g_deltas [max_pos, 6], g_logits [max_pos + max_neg, C]. */
+int nnd_head_loss_fwd(const float* logits, const float* deltas, const float* anchors, long long A, int C, const long long* matches,
+                      const float* gt_boxes, const int* gt_off, const float* labels, const long long* pos_idx,
+                      const long long* neg_idx, const int* counts, float xform_clip, float giou_eps, float* losses_out,
+                      float* g_deltas, float* g_logits, cudaStream_t stream);
+int nnd_head_loss_bwd(const float* g_deltas, const float* g_logits, int C, const long long* pos_idx, const long long* neg_idx,
+                      const int* counts, const float* up_reg, const float* up_cls, float* d_deltas /* zeroed [n,6] */,
+                      float* d_logits /* zeroed [n,C] */, cudaStream_t stream);
+
+/* ---- detection post-processing per image.  Replaces postprocess_detections_single_image (nndet/core/retina.py:332-379) +
+ *      batched_nms (nndet/core/boxes/nms.py:81-106).  boxes [B*A, 6] decoded+clipped, probs [B*A*C]; out_* [B, det, ...]. */
+size_t nnd_detect_postprocess_workspace_bytes(long long A, int C, int topk);
+int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long long A, int C, int topk, float score_thresh,
+                           int use_score_thresh, float min_size, int use_min_size, float nms_thresh, int det_per_img,
+                           float* out_boxes, float* out_scores, long long* out_labels, int* out_counts, void* ws,
+                           size_t ws_bytes, cudaStream_t stream);
+
+/* ---- convolutions.  Replace torch.nn.Conv3d / ConvTranspose3d (cuDNN) as built by nd_conv, nndet/arch/conv.py:297-348, and their
+ *      autograd.  Activations NDHWC bf16; geom_host: int[21 + 4*T] describing one "gather convolution" launch
+ *      (csrc/conv_common.cuh): N,Di,Hi,Wi,Cin, Ld,Lh,Lw, sd,sh,sw, Do,Ho,Wo, omd,omh,omw, ood,ooh,oow, T, then per tap
+ *      (off_d, off_h, off_w, weight_tap).  w: bf16 [T][CoutPad][Cin] from nnd_pack_weights.  Epilogue: +bias, +residual,
+ *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
+ *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 1 if the tcgen05 kernel ran. */
+void nnd_conv_set_tensor_path(int enable_tcgen05);
+int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
+                         long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
+                         const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);
+/* dW[co*s_co + ci*s_ci + tap*s_tap] += sum_voxels dy[.., co] * x[.., ci]   (fp32, caller zero-fills) */
+int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom_host, float* dw, long long s_co,
+                        long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t stream);
+/* image-input layer (Cin <= 4): x fp32 NCDHW, w fp32 [Cout][Cin][T] */
+int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom_host, int Cout, void* out, float* stat_sum,
+                             float* stat_sq, cudaStream_t stream);
+int nnd_conv_first_wgrad_f32(const float* x, const void* dy, const int* geom_host, int Cout, float* dw, cudaStream_t stream);
+/* fp32 master weight ([Cout][Cin][T], or [Cin][Cout][T] if transposed) -> bf16 fprop / dgrad operands */
+int nnd_pack_weights(const float* w, int Cout, int Cin, int T, int transposed, void* fwd, int CoutPadF, int CinPadF, void* bwd,
+                     int CinPadB, int CoutPadB, cudaStream_t stream);
+
+/* ---- instance / group norm (+affine, +ReLU).  Replace nn.InstanceNorm3d / GroupNorm / ReLU (nndet/arch/conv.py:388-446,
+ *      nndet/arch/layers/norm.py:26-50).  stats from the conv epilogue; a, b, mean, rstd: [N, C] fp32. */
+int nnd_norm_finalize(const float* ssum, const float* ssq, const float* gamma, const float* beta, int N, int C, int cpg,
+                      long long count, float eps, float* a, float* b, float* mean, float* rstd, cudaStream_t stream);
+int nnd_norm_apply(const void* y, const float* a, const float* b, int N, long long V, int C, int relu, void* z, cudaStream_t stream);
+int nnd_norm_backward(const void* dz, const void* y, const float* a, const float* b, const float* mean, const float* rstd,
+                      const float* gamma, int N, long long V, int C, int cpg, int relu, void* dy, float* dgamma, float* dbeta,
+                      float* ws /* 5*N*C floats */, cudaStream_t stream);
+
+/* ---- segmentation head.  Replace DiCESegmenterFgBg (nndet/arch/heads/segmenter.py:223-290) + SoftDiceLoss / CE
+ *      (nndet/losses/segmentation.py:84-151).  x bf16 [total, C]; logits fp32 [total, 2]; target fp32 [total]. */
+int nnd_seg_conv_fwd(const void* x, int C, const float* w, const float* bias, long long total, float* logits, cudaStream_t stream);
+int nnd_seg_loss_fwd(const float* logits, const float* target, long long total, float alpha, float smooth, double* sums4,
+                     float* losses_out2, cudaStream_t stream);
+int nnd_seg_loss_bwd(const float* logits, const float* target, const double* sums4, long long total, float alpha, float smooth,
+                     const float* up_ce, const float* up_dice, float* dlogits, cudaStream_t stream);
+int nnd_seg_conv_bwd(const void* x, int C, const float* w, const float* dlogits, long long total, void* dx, float* dw, float* db,
+                     cudaStream_t stream);
+
+/* ---- optimizer + small streaming helpers.  nnd_sgd_step == torch.optim.SGD(momentum, nesterov, weight_decay) as configured in
+ *      nndet/ptmodule/retinaunet/base.py:300-336; elements >= n_decay get no weight decay (norm params). */
+int nnd_sgd_step(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
+                 int nesterov, int first_step, float grad_scale, cudaStream_t stream);
+int nnd_pad_cast_f32_bf16(const float* src, int N, long long rows, int C, long long src_n_stride, const float* mul, void* dst,
+                          int Cpad, cudaStream_t stream);
+int nnd_channel_sum(const void* src, int is_bf16, long long rows, int C, long long stride, float scale, float* out, cudaStream_t stream);
+int nnd_cast_f32_bf16(const float* s, void* d, long long n, cudaStream_t stream);
+int nnd_scale_grad(const float* g, const float* out, int N, long long len, long long n_stride, const float* scale, float* dscale,
+                   cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNDET_B200_H */

@@ -7,7 +7,11 @@ namespace {
 thread_local char g_err[512] = "";
 }
 
+unsigned long long g_nnd_launches = 0;
+
 extern "C" {
+
+unsigned long long nnd_launch_count(void) { return g_nnd_launches; }
 
 int nnd_set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where ? where : "?", cudaGetErrorName(e), cudaGetErrorString(e));

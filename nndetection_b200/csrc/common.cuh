@@ -12,6 +12,7 @@
 #define NND_ERR_CUDA 3         // a CUDA runtime call / launch failed (see nnd_last_cuda_error)
 
 extern "C" int nnd_set_cuda_error(cudaError_t e, const char* where);
+extern unsigned long long g_nnd_launches;       // kernels launched through the C ABI (bench.py: gpu_launches)
 
 #define NND_CUDA_TRY(expr)                                              \
   do {                                                                  \
@@ -21,6 +22,7 @@ extern "C" int nnd_set_cuda_error(cudaError_t e, const char* where);
 
 #define NND_LAUNCH_CHECK(name)                                          \
   do {                                                                  \
+    ++g_nnd_launches;                                                   \
     cudaError_t _e = cudaGetLastError();                                \
     if (_e != cudaSuccess) return nnd_set_cuda_error(_e, name);         \
   } while (0)

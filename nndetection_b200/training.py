@@ -1,0 +1,100 @@
+"""Training-step plumbing for the hot path: flat parameter / gradient buffers, one fused SGD kernel, the reference's
+LR schedule, and patch-level data parallelism (one process per GPU, NCCL all-reduce on the gradient buffer only).
+
+Reference semantics kept: torch.optim.SGD(nesterov, momentum 0.9, weight decay 3e-5 on everything except norm
+parameters) -- nndet/ptmodule/retinaunet/base.py:300-336, nndet/training/optimizer/utils.py:30-50; LinearWarmupPolyLR --
+nndet/training/learning_rate.py; DDP is what PL would do for `gpus > 1` (scripts/train.py:265-272): per-GPU batch,
+gradient mean over ranks, no other collective (InstanceNorm / GroupNorm are per sample).
+"""
+from ctypes import c_float, c_int, c_longlong
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib as L
+from .arch.conv import NormParams, bump_weights_epoch
+
+
+class FlatParameters:
+    """Re-homes every parameter of `model` into ONE fp32 buffer ([decayed | norm (no decay)]) and every gradient
+    into a matching buffer, so the optimizer is one launch and the DDP exchange one NCCL call."""
+
+    def __init__(self, model: nn.Module):
+        norm_ids = set()
+        for m in model.modules():
+            if isinstance(m, NormParams):
+                for p in m.parameters(recurse=False):
+                    norm_ids.add(id(p))
+        params = [p for p in model.parameters() if p.requires_grad]
+        decay = [p for p in params if id(p) not in norm_ids]
+        no_decay = [p for p in params if id(p) in norm_ids]
+        self.params = decay + no_decay
+        self.n_decay = sum(p.numel() for p in decay)
+        self.n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.mom = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)         # autograd accumulates in place into the flat buffer
+            off += k
+        self.first_step = True
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+def poly_lr(step: int, initial_lr: float, warm_iterations: int, warm_lr: float, poly_gamma: float, num_iterations: int) -> float:
+    """LinearWarmupPolyLR (nndet/training/learning_rate.py): linear warm-up from warm_lr, then polynomial decay."""
+    if step < warm_iterations:
+        return warm_lr + (initial_lr - warm_lr) * step / max(1, warm_iterations)
+    t = (step - warm_iterations) / max(1, num_iterations - warm_iterations)
+    return initial_lr * (1 - min(t, 1.0)) ** poly_gamma
+
+
+class Trainer:
+    """Full train step = forward + losses (+ optional detection post-processing) + backward + gradient all-reduce +
+    SGD.  Nothing in here synchronises with the host; `losses` are device tensors (the reference's caller reads
+    them with .item(), nndet/ptmodule/retinaunet/base.py:154)."""
+
+    def __init__(self, model: nn.Module, initial_lr=0.01, momentum=0.9, nesterov=True, weight_decay=3e-5,
+                 warm_iterations=4000, warm_lr=1e-6, poly_gamma=0.9, num_iterations=50 * 2500, distributed: bool = False):
+        self.model = model
+        self.fp = FlatParameters(model)
+        self.cfg = dict(initial_lr=initial_lr, warm_iterations=warm_iterations, warm_lr=warm_lr, poly_gamma=poly_gamma,
+                        num_iterations=num_iterations)
+        self.momentum, self.nesterov, self.weight_decay = momentum, nesterov, weight_decay
+        self.step_idx = 0
+        self.distributed = distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.distributed else 1
+        if self.distributed:
+            dist.broadcast(self.fp.flat, src=0)
+            bump_weights_epoch()
+
+    def optimizer_step(self):
+        fp = self.fp
+        lr = poly_lr(self.step_idx, **self.cfg)
+        L.check(L.lib().nnd_sgd_step(L.ptr(fp.flat), L.ptr(fp.grad), L.ptr(fp.mom), c_longlong(fp.n), c_longlong(fp.n_decay),
+                                     c_float(lr), c_float(self.momentum), c_float(self.weight_decay),
+                                     c_int(1 if self.nesterov else 0), c_int(1 if fp.first_step else 0),
+                                     c_float(1.0 / self.world), L.stream_ptr()), "nnd_sgd_step")
+        fp.first_step = False
+        self.step_idx += 1
+        bump_weights_epoch()              # packed bf16 weight copies are refreshed lazily by the layers
+
+    def train_step(self, images: torch.Tensor, targets: dict, evaluation: bool = False):
+        self.model.train()
+        self.fp.zero_grad()
+        losses, prediction = self.model.train_step(images, targets, evaluation=evaluation, batch_num=self.step_idx)
+        loss = sum(losses.values())
+        loss.backward()
+        if self.distributed:
+            dist.all_reduce(self.fp.grad)      # 76 MB fp32, NCCL over NVLink; mean folded into the SGD kernel
+        self.optimizer_step()
+        return losses, prediction
