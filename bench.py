@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="luna")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -230,6 +231,10 @@ def main():
     launches = lib.nnd_launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}), flush=True)
+        return
     # ---- timed region 2: end to end through the public API with host buffers
     for i in range(2):
         step_e2e(i)
