@@ -72,50 +72,74 @@ conv_first_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w
   }
 }
 
-// dW[co][ci][tap] += sum_v dy[v][co] * x[v + off_tap][ci].  Warps split the taps, lanes are output channels.
-__global__ void __launch_bounds__(256)
+// dW[co][ci][tap] += sum_v dy[v][co] * x[v + off_tap][ci].
+// One CTA = ROWS consecutive output rows (fixed n, d; h0..h0+ROWS-1).  Warp = one (dz, dy) pair of the filter, lane =
+// output channel; the three dx taps slide along w in registers, so a voxel costs 2 shared loads + 3 FMAs per thread.
+// dy row tile (bf16) and the 9 input rows it needs (fp32, w-halo included) are staged in shared memory per row.
+constexpr int FW_ROWS = 8;
+__global__ void __launch_bounds__(288)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, const ConvGeom g, int Cout,
-                        int chunk, float* __restrict__ dw) {
-  constexpr int MAXT = 4;                       // taps per warp (8 warps * 4 >= 27)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int V = g.Ld * g.Lh * g.Lw;
-  const int n = blockIdx.y;
-  const int v0 = blockIdx.x * chunk, v1 = min(v0 + chunk, V);
-  const size_t plane = (size_t)g.Di * g.Hi * g.Wi;
-  const float* xn = x + (size_t)n * g.Cin * plane;
+                        float* __restrict__ dw) {
+  extern __shared__ unsigned char fsm[];
+  const int W = g.Lw, H = g.Lh, D = g.Ld;
+  float* sx = reinterpret_cast<float*>(fsm);                           // [9][W + 2]
+  __nv_bfloat16* sdy = reinterpret_cast<__nv_bfloat16*>(sx + 9 * (W + 2));   // [W][32]
+  __shared__ int s_tap[27];                                            // weight tap index of (dz,dy,dx) or -1
+  if (threadIdx.x < 27) s_tap[threadIdx.x] = -1;
+  __syncthreads();
+  if (threadIdx.x < g.T) {
+    const int t = threadIdx.x;
+    s_tap[((g.off_d[t] + 1) * 3 + (g.off_h[t] + 1)) * 3 + (g.off_w[t] + 1)] = g.tap_w[t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;         // warp 0..8 = (dz+1)*3 + (dy+1)
+  const int dz = warp / 3 - 1, dyo = warp % 3 - 1;
+  const int t0 = s_tap[warp * 3 + 0], t1 = s_tap[warp * 3 + 1], t2 = s_tap[warp * 3 + 2];
+  const int rows_per_d = (H + FW_ROWS - 1) / FW_ROWS;
+  const int n = blockIdx.x / (D * rows_per_d);
+  const int rem = blockIdx.x % (D * rows_per_d);
+  const int d = rem / rows_per_d, h0 = (rem % rows_per_d) * FW_ROWS;
+  const size_t plane = (size_t)D * H * W;
   for (int cb = 0; cb < Cout; cb += 32) {
-    const int co = cb + lane;
-    float acc[MAXT][FIRST_MAX_CIN];
-#pragma unroll
-    for (int i = 0; i < MAXT; ++i)
-#pragma unroll
-      for (int j = 0; j < FIRST_MAX_CIN; ++j) acc[i][j] = 0.f;
-    for (int v = v0; v < v1; ++v) {
-      const float d = co < Cout ? __bfloat162float(dy[((size_t)n * V + v) * Cout + co]) : 0.f;
-      const int lw = v % g.Lw; const int r = v / g.Lw; const int lh = r % g.Lh; const int ld = r / g.Lh;
-#pragma unroll
-      for (int i = 0; i < MAXT; ++i) {
-        const int t = warp + i * 8;
-        if (t >= g.T) break;
-        const int id = ld + g.off_d[t], ih = lh + g.off_h[t], iw = lw + g.off_w[t];
-        if ((unsigned)id >= (unsigned)g.Di || (unsigned)ih >= (unsigned)g.Hi || (unsigned)iw >= (unsigned)g.Wi) continue;
-        const size_t pos = ((size_t)id * g.Hi + ih) * g.Wi + iw;
-#pragma unroll
-        for (int ci = 0; ci < FIRST_MAX_CIN; ++ci)
-          if (ci < g.Cin) acc[i][ci] = fmaf(d, __ldg(xn + ci * plane + pos), acc[i][ci]);
+    for (int ci = 0; ci < g.Cin; ++ci) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      const float* xp = x + ((size_t)n * g.Cin + ci) * plane;
+      for (int hr = 0; hr < FW_ROWS && h0 + hr < H; ++hr) {
+        const int h = h0 + hr;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * (W + 2); i += blockDim.x) {
+          const int r = i / (W + 2), wx = i % (W + 2) - 1;
+          const int zz = d + r / 3 - 1, yy = h + r % 3 - 1;
+          float v = 0.f;
+          if ((unsigned)zz < (unsigned)D && (unsigned)yy < (unsigned)H && (unsigned)wx < (unsigned)W)
+            v = __ldg(xp + ((size_t)zz * H + yy) * W + wx);
+          sx[i] = v;
+        }
+        const __nv_bfloat16* dyr = dy + (((size_t)n * D + d) * H + h) * W * Cout + cb;
+        for (int i = threadIdx.x; i < W * 32; i += blockDim.x) {
+          const int wv = i >> 5, c = i & 31;
+          sdy[i] = (cb + c < Cout) ? dyr[(size_t)wv * Cout + c] : __float2bfloat16(0.f);
+        }
+        __syncthreads();
+        const float* xr = sx + warp * (W + 2);       // row (dz, dy), index w + 1 + dx
+        float xm = xr[0], xc = xr[1];
+        for (int wv = 0; wv < W; ++wv) {
+          const float xn = xr[wv + 2];
+          const float dv = __bfloat162float(sdy[wv * 32 + lane]);
+          a0 = fmaf(dv, xm, a0); a1 = fmaf(dv, xc, a1); a2 = fmaf(dv, xn, a2);
+          xm = xc; xc = xn;
+        }
       }
-    }
-    if (co < Cout) {
-#pragma unroll
-      for (int i = 0; i < MAXT; ++i) {
-        const int t = warp + i * 8;
-        if (t >= g.T) break;
-#pragma unroll
-        for (int ci = 0; ci < FIRST_MAX_CIN; ++ci)
-          if (ci < g.Cin) atomicAdd(&dw[((size_t)co * g.Cin + ci) * g.T + g.tap_w[t]], acc[i][ci]);
+      const int co = cb + lane;
+      if (co < Cout) {
+        float* base = dw + ((size_t)co * g.Cin + ci) * g.T;
+        if (t0 >= 0) atomicAdd(base + t0, a0);
+        if (t1 >= 0) atomicAdd(base + t1, a1);
+        if (t2 >= 0) atomicAdd(base + t2, a2);
       }
     }
   }
+  (void)dz; (void)dyo;
 }
 
 }  // namespace
@@ -137,12 +161,15 @@ int nnd_conv_first_fprop(const float* x, const float* w, const ConvGeom& g, int 
 }
 
 int nnd_conv_first_wgrad(const float* x, const __nv_bfloat16* dy, const ConvGeom& g, int Cout, float* dw, cudaStream_t st) {
-  if (!x || !dy || !dw || g.Cin < 1 || g.Cin > FIRST_MAX_CIN || g.T > 32) return NND_ERR_ARG;
-  const int V = g.Ld * g.Lh * g.Lw;
-  int chunk = 2048;
-  while (chunk > 128 && (long long)((V + chunk - 1) / chunk) * g.N < NND_NUM_SMS * 4) chunk >>= 1;
-  dim3 grid((V + chunk - 1) / chunk, g.N);
-  conv_first_wgrad_kernel<<<grid, 256, 0, st>>>(x, dy, g, Cout, chunk, dw);
+  if (!x || !dy || !dw || g.Cin < 1 || g.Cin > FIRST_MAX_CIN || g.T > 27) return NND_ERR_ARG;
+  for (int t = 0; t < g.T; ++t)
+    if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return NND_ERR_ARG;
+  const int rows_per_d = (g.Lh + FW_ROWS - 1) / FW_ROWS;
+  const unsigned blocks = (unsigned)(g.N * g.Ld * rows_per_d);
+  const size_t smem = (size_t)9 * (g.Lw + 2) * sizeof(float) + (size_t)g.Lw * 32 * sizeof(__nv_bfloat16);
+  if (smem > 200 * 1024) return NND_ERR_ARG;
+  if (smem > 48 * 1024) NND_CUDA_TRY(cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_first_wgrad_kernel<<<blocks, 288, smem, st>>>(x, dy, g, Cout, dw);
   NND_LAUNCH_CHECK("conv_first_wgrad_kernel");
   return NND_OK;
 }

@@ -1,4 +1,391 @@
-// tcgen05 / TMA convolution kernel for the 3x3x3 stride-1 layers -- placeholder until the kernel lands.
+// 3x3x3 (or any taps with offsets in [-1, 1]) stride-1 gather convolution on the 5th-generation tensor cores.
+//
+// This is the im2col-free kernel for the layers that carry ~90 % of the network's convolution FLOPs (fprop of every
+// stride-1 3x3x3 conv and, with flipped taps + transposed weights, their dgrad).  It replaces cuDNN implicit GEMM as
+// invoked by torch.nn.Conv3d in the reference (nndet/arch/conv.py:344-348).
+//
+// Data movement (per CTA tile = MT depth slices x 16 x 8 voxels x N_TILE output channels):
+//   * the input HALO ((MT+2) x 18 x 10 voxels x 32 channels) is staged ONCE per 32-channel chunk and serves all 27
+//     taps: smem layout [channel group of 8][z][y][x][8 ch] -- one voxel = one 16-byte core-matrix row, so the UMMA
+//     shared-memory descriptor of tap (dz,dy,dx) is just the halo base + ((dz+1)*18 + (dy+1))*10 + (dx+1) rows:
+//     K-major, no swizzle, SBO = 160 B (halo row pitch), LBO = channel-group pitch.  No im2col, no per-tap reload.
+//   * the weight slice of one (tap, 32-channel chunk) [N_TILE x 32] streams through a 6-slot ring in the canonical
+//     K-major no-swizzle layout [k group][n][8] (SBO 128 B, LBO N_TILE*16 B) and is shared by the MT slice-MMAs.
+//   * accumulators live in TMEM: MT x N_TILE fp32 columns, double buffered so the epilogue of tile i overlaps the
+//     MMAs of tile i+1.
+// Roles (288 threads): warps 0-3 producers (cp.async 16-byte gathers with zero fill = padding; completion ->
+// fence.proxy.async -> mbarrier), warp 4 lane 0 issues tcgen05.mma / tcgen05.commit, warps 5-8 epilogue
+// (tcgen05.ld -> bias / residual / scale -> bf16 -> 64-byte row stores, per-(sample, channel) norm statistics via a
+// warp transpose-reduce).  Persistent grid = #SMs, static round-robin tiles.
 #include "conv_common.cuh"
-int nnd_conv_tc_supported(const ConvGeom&, const ConvEpilogue&) { return 0; }
-int nnd_conv_tc(const __nv_bfloat16*, const __nv_bfloat16*, const ConvGeom&, const ConvEpilogue&, cudaStream_t) { return NND_ERR_ARG; }
+
+namespace {
+
+constexpr int BH = 16, BW = 8;                   // tile = MT x 16 x 8 voxels (one 128-row MMA per depth slice)
+constexpr int HY = BH + 2, HX = BW + 2;          // halo extents in h, w
+constexpr int ROW_PITCH = HX * 16;               // 160 B
+constexpr int SLICE_PITCH = HY * ROW_PITCH;      // 2880 B
+constexpr int KG = 4;                            // channel groups (of 8) per stage = 32 channels
+constexpr int A_STAGES = 2, B_SLOTS = 6, LAG = 3;
+constexpr int NUM_PROD = 128;
+constexpr int TC_THREADS = 288;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                       unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcTiles {
+  int DB, HB, WB, NT;       // tile counts along d, h, w and output-channel tiles
+  int total;
+};
+
+// lane l ends with the sum over the warp's 32 lanes of v[l'] for column l' = bit-reversal-free mapping: the column
+// index kept by a lane at the end is returned in `col`.
+__device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane, int& col) {
+  int base = 0;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[j] = (upper ? v[j + s] : v[j]) + recv;
+    }
+    if (upper) base += s;
+  }
+  col = base;
+  return v[0];
+}
+
+template <int N_TILE, int MT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
+               const ConvEpilogue ep, const TcTiles tl) {
+  constexpr int HALO_SLICES = MT + 2;
+  constexpr int HV = HALO_SLICES * HY * HX;                 // halo voxels per channel group
+  constexpr int A_BYTES = KG * HV * 16;
+  constexpr int B_BYTES = N_TILE * KG * 16;
+  constexpr unsigned LBO_A = HV * 16, SBO_A = ROW_PITCH;
+  constexpr unsigned LBO_B = N_TILE * 16, SBO_B = 128;
+  constexpr int ACC_COLS = MT * N_TILE;                     // one accumulator stage
+  constexpr int TMEM_COLS = 2 * ACC_COLS >= 512 ? 512 : (2 * ACC_COLS >= 256 ? 256 : (2 * ACC_COLS >= 128 ? 128 : 64));
+  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  constexpr unsigned IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sA = smem;                                  // A_STAGES x A_BYTES
+  unsigned char* sB = smem + A_STAGES * A_BYTES;             // B_SLOTS x B_BYTES
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + B_SLOTS * B_BYTES);
+  // barrier map: [0,B_SLOTS) fullB | [B_SLOTS, 2B) emptyB | +A_STAGES emptyA | +2 tmem_full | +2 tmem_empty
+  __shared__ unsigned s_tmem_base;
+  __shared__ int s_tapoff[NND_MAX_TAPS];
+  __shared__ float s_stat[2][4][N_TILE];
+  const unsigned bar0 = smem_u32(bars);
+  auto FULLB = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTYB = [&](int i) { return bar0 + 8u * (B_SLOTS + i); };
+  auto EMPTYA = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + i); };
+  auto TFULL = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + i); };
+  auto TEMPTY = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + 2 + i); };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KC = g.Cin / 32, T = g.T;
+
+  if (tid == 0) {
+    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD); mbar_init(EMPTYB(i), 1); }
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(EMPTYA(i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < T) s_tapoff[tid] = (((g.off_d[tid] + 1) * HY + (g.off_h[tid] + 1)) * HX + (g.off_w[tid] + 1)) * 16;
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = s_tmem_base;
+
+  auto decode_tile = [&](int tile, int& n, int& d0, int& h0, int& w0, int& nt) {
+    nt = tile % tl.NT; int r = tile / tl.NT;
+    const int wb = r % tl.WB; r /= tl.WB;
+    const int hb = r % tl.HB; r /= tl.HB;
+    const int db = r % tl.DB; n = r / tl.DB;
+    d0 = db * MT; h0 = hb * BH; w0 = wb * BW;
+  };
+
+  if (warp < 4) {
+    // ================================================================ producers
+    unsigned slot = 0, slot_phase = 0;            // B ring cursor (issue side)
+    unsigned astage = 0, a_phase = 0;             // A double buffer cursor
+    unsigned done_slot = 0;                       // completion cursor (LAG items behind)
+    int pending = 0;
+    for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+      int n, d0, h0, w0, nt;
+      decode_tile(tile, n, d0, h0, w0, nt);
+      const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin;
+      for (int kc = 0; kc < KC; ++kc) {
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(EMPTYB(slot), slot_phase ^ 1);
+          if (t == 0) {
+            mbar_wait(EMPTYA(astage), a_phase ^ 1);
+            const unsigned a_base = smem_u32(sA + astage * A_BYTES);
+            for (int i = tid; i < KG * HV; i += NUM_PROD) {
+              const int gidx = i / HV; int r = i - gidx * HV;
+              const int z = r / (HY * HX); r -= z * (HY * HX);
+              const int y = r / HX; const int x = r - y * HX;
+              const int d = d0 - 1 + z, h = h0 - 1 + y, w = w0 - 1 + x;
+              const bool ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi && (unsigned)w < (unsigned)g.Wi;
+              const __nv_bfloat16* src = ok ? in_n + ((size_t)(d * g.Hi + h) * g.Wi + w) * g.Cin + kc * 32 + gidx * 8 : in;
+              cp_async16(a_base + i * 16, src, ok);
+            }
+          }
+          {
+            const unsigned b_base = smem_u32(sB + slot * B_BYTES);
+            const __nv_bfloat16* wsrc = wgt + ((size_t)g.tap_w[t] * ep.CoutPad + nt * N_TILE) * g.Cin + kc * 32;
+            for (int i = tid; i < N_TILE * KG; i += NUM_PROD) {
+              const int kg = i / N_TILE, nr = i - kg * N_TILE;
+              cp_async16(b_base + i * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
+            }
+          }
+          cp_async_commit();
+          ++pending;
+          if (pending > LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async();
+            mbar_arrive(FULLB(done_slot));
+            done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
+            --pending;
+          }
+          if (t == T - 1) { astage ^= 1; if (astage == 0) a_phase ^= 1; }
+          if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (pending > 0) {
+      mbar_arrive(FULLB(done_slot));
+      done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
+      --pending;
+    }
+  } else if (warp == 4) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      unsigned slot = 0, slot_phase = 0, astage = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+        mbar_wait(TEMPTY(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const unsigned d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kc = 0; kc < KC; ++kc) {
+          const unsigned a_base = smem_u32(sA + astage * A_BYTES);
+          for (int t = 0; t < T; ++t) {
+            mbar_wait(FULLB(slot), slot_phase);
+            tc_fence_after();
+            const unsigned b_base = smem_u32(sB + slot * B_BYTES);
+            const unsigned a_tap = a_base + (unsigned)s_tapoff[t];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+              for (int k16 = 0; k16 < 2; ++k16) {
+                const unsigned long long ad = make_desc(a_tap + mt * SLICE_PITCH + k16 * 2 * LBO_A, LBO_A, SBO_A);
+                const unsigned long long bd = make_desc(b_base + k16 * 2 * LBO_B, LBO_B, SBO_B);
+                tc_mma(d_tmem + mt * N_TILE, ad, bd, IDESC, (kc | t | k16) != 0 ? 1u : 0u);
+              }
+            }
+            tc_commit(EMPTYB(slot));
+            if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
+          }
+          tc_commit(EMPTYA(astage));
+          astage ^= 1;
+        }
+        tc_commit(TFULL(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 5..8 -> TMEM lane quarter warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // MMA row = TMEM lane = voxel (hy, wx) of a slice
+    const int hy = row >> 3, wx = row & 7;
+    const float scale = ep.scale ? *ep.scale : 1.f;
+    const bool do_stats = ep.stat_sum != nullptr;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
+    unsigned acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+      int n, d0, h0, w0, nt;
+      decode_tile(tile, n, d0, h0, w0, nt);
+      const int h = h0 + hy, w = w0 + wx;
+      const bool hw_ok = h < g.Hi && w < g.Wi;
+      mbar_wait(TFULL(acc), acc_phase);
+      tc_fence_after();
+      float ssum[N_TILE / 32], ssq[N_TILE / 32];
+#pragma unroll
+      for (int c = 0; c < N_TILE / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+      int stat_col = 0;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int d = d0 + mt;
+        const bool ok = hw_ok && d < g.Di;
+        const long long vox = ((long long)(n * g.Di + d) * g.Hi + h) * g.Wi + w;
+#pragma unroll
+        for (int c = 0; c < N_TILE / 32; ++c) {
+          unsigned v[32];
+          tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + acc * ACC_COLS + mt * N_TILE + c * 32, v);
+          const int co0 = nt * N_TILE + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += ep.bias[co0 + j];
+          }
+          if (ep.residual && ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + vox * ep.Cout + co0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = rp[u];
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 t2 = __bfloat1622float2(hp[k]);
+                f[u * 8 + 2 * k] += t2.x; f[u * 8 + 2 * k + 1] += t2.y;
+              }
+            }
+          }
+          __align__(16) __nv_bfloat162 pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            pk[j] = __floats2bfloat162_rn(f[2 * j] * scale, f[2 * j + 1] * scale);
+            const float2 r2 = __bfloat1622float2(pk[j]);
+            f[2 * j] = ok ? r2.x : 0.f; f[2 * j + 1] = ok ? r2.y : 0.f;
+          }
+          if (ok) {
+            uint4* op = reinterpret_cast<uint4*>(outp + vox * ep.Cout + co0);
+            const uint4* sp = reinterpret_cast<const uint4*>(pk);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) op[u] = sp[u];
+          }
+          if (do_stats) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            int col;
+            ssum[c] += warp_transpose_reduce32(f, lane, col);
+            ssq[c] += warp_transpose_reduce32(sq, lane, col);
+            stat_col = col;
+          }
+        }
+      }
+      // accumulator drained -> hand the TMEM stage back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      if (do_stats) {
+#pragma unroll
+        for (int c = 0; c < N_TILE / 32; ++c) { s_stat[0][q][c * 32 + stat_col] = ssum[c]; s_stat[1][q][c * 32 + stat_col] = ssq[c]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - 5 * 32;               // 0..127
+        for (int ch = et; ch < N_TILE; ch += 128) {
+          const float s = s_stat[0][0][ch] + s_stat[0][1][ch] + s_stat[0][2][ch] + s_stat[0][3][ch];
+          const float qq = s_stat[1][0][ch] + s_stat[1][1][ch] + s_stat[1][2][ch] + s_stat[1][3][ch];
+          atomicAdd(&ep.stat_sum[(size_t)n * ep.Cout + nt * N_TILE + ch], s);
+          atomicAdd(&ep.stat_sq[(size_t)n * ep.Cout + nt * N_TILE + ch], qq);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+template <int N_TILE, int MT>
+int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+  TcTiles tl;
+  tl.DB = (g.Di + MT - 1) / MT; tl.HB = (g.Hi + BH - 1) / BH; tl.WB = (g.Wi + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
+  tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
+  constexpr int HV = (MT + 2) * HY * HX;
+  const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
+  conv_tc_kernel<N_TILE, MT><<<grid, TC_THREADS, smem, st>>>(in, w, g, ep, tl);
+  NND_LAUNCH_CHECK("conv_tc_kernel");
+  return NND_OK;
+}
+
+}  // namespace
+
+int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1) return 0;
+  if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
+  if (g.Ld != g.Di || g.Lh != g.Hi || g.Lw != g.Wi || g.Do != g.Di || g.Ho != g.Hi || g.Wo != g.Wi) return 0;
+  if (g.T < 9 || g.Cin % 32) return 0;
+  for (int t = 0; t < g.T; ++t)
+    if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
+  if (ep.out_fp32 || ep.Cout % 32 || ep.CoutPad != ep.Cout) return 0;
+  if (ep.out_v_stride != ep.Cout || ep.out_n_stride != (long long)g.Do * g.Ho * g.Wo * ep.Cout) return 0;
+  if (g.Hi < 8 || g.Wi < 8) return 0;
+  return 1;
+}
+
+int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+  if (!nnd_conv_tc_supported(g, ep)) return NND_ERR_ARG;
+  if (ep.Cout % 128 == 0) return launch_tc<128, 2>(in, w, g, ep, st);
+  if (ep.Cout % 64 == 0) return launch_tc<64, 4>(in, w, g, ep, st);
+  return launch_tc<32, 4>(in, w, g, ep, st);
+}

@@ -150,13 +150,21 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       int pos = count0 + __popcll(km & ((1ull << threadIdx.x) - 1ull));
       keep_out[pos] = (long long)order[base + threadIdx.x];
     }
+    // OR the mask rows of this block's kept boxes into remv[c], c > b.  Loads are independent: issue them in
+    // batches of 8 so the L2/HBM latency is paid once per batch, not once per kept row.
     for (int c = b + 1 + threadIdx.x; c < col_blocks; c += blockDim.x) {
       unsigned long long acc = remv[c], m = km;
       const unsigned long long* col = mask + (size_t)base * col_blocks + c;
       while (m) {
-        int j = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        acc |= col[(size_t)j * col_blocks];
+        unsigned long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = m ? __ffsll((long long)m) - 1 : -1;
+          m &= m - 1;                                    // 0 stays 0
+          v[u] = j >= 0 ? __ldg(col + (size_t)j * col_blocks) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc |= v[u];
       }
       remv[c] = acc;
     }
