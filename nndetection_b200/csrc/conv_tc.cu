@@ -13,8 +13,8 @@
 //     K-major no-swizzle layout [k group][n][8] (SBO 128 B, LBO N_TILE*16 B) and is shared by the MT slice-MMAs.
 //   * accumulators live in TMEM: MT x N_TILE fp32 columns, double buffered so the epilogue of tile i overlaps the
 //     MMAs of tile i+1.
-// Roles (288 threads): warps 0-3 producers (cp.async 16-byte gathers with zero fill = padding; completion ->
-// fence.proxy.async -> mbarrier), warp 4 lane 0 issues tcgen05.mma / tcgen05.commit, warps 5-8 epilogue
+// Roles: warps 0-3 producers (cp.async 16-byte gathers with zero fill = padding; completion ->
+// fence.proxy.async -> mbarrier), MT issuer warps (lane 0 issues tcgen05.mma / tcgen05.commit for its depth slice), 4 epilogue warps
 // (tcgen05.ld -> bias / residual / scale -> bf16 -> 64-byte row stores, per-(sample, channel) norm statistics via a
 // warp transpose-reduce).  Persistent grid = #SMs, static round-robin tiles.
 #include "conv_common.cuh"
@@ -26,9 +26,9 @@ constexpr int HY = BH + 2, HX = BW + 2;          // halo extents in h, w
 constexpr int ROW_PITCH = HX * 16;               // 160 B
 constexpr int SLICE_PITCH = HY * ROW_PITCH;      // 2880 B
 constexpr int KG = 4;                            // channel groups (of 8) per stage = 32 channels
-constexpr int A_STAGES = 2, B_SLOTS = 6, LAG = 3;
+constexpr int A_STAGES = 2, B_SLOTS = 12, LAG = 6;
 constexpr int NUM_PROD = 128;
-constexpr int TC_THREADS = 288;
+constexpr int tc_threads(int mt) { return (4 + mt + 4) * 32; }   // 4 producer + MT issuer + 4 epilogue warps
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -45,6 +45,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}"
       ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -102,7 +111,7 @@ __device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane, int
 }
 
 template <int N_TILE, int MT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(MT), 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
                const ConvEpilogue ep, const TcTiles tl) {
   constexpr int HALO_SLICES = MT + 2;
@@ -135,9 +144,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   const int KC = g.Cin / 32, T = g.T;
 
   if (tid == 0) {
-    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD); mbar_init(EMPTYB(i), 1); }
-    for (int i = 0; i < A_STAGES; ++i) mbar_init(EMPTYA(i), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 4); }
+    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD); mbar_init(EMPTYB(i), MT); }
+    for (int i = 0; i < A_STAGES; ++i) mbar_init(EMPTYA(i), MT);
+    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), MT); mbar_init(TEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < T) s_tapoff[tid] = (((g.off_d[tid] + 1) * HY + (g.off_h[tid] + 1)) * HX + (g.off_w[tid] + 1)) * 16;
@@ -160,50 +169,81 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
 
   if (warp < 4) {
     // ================================================================ producers
+    // Work is a flat sequence of chunks = (tile, 32-channel block); each chunk has T items (taps).  Item t of a chunk
+    // carries the weight slice of tap t; the HALO of the NEXT chunk is prefetched in the middle of the current one
+    // (item T/2) so it has landed long before its first tap is due.  Halo loads are issued row-wise: one thread owns
+    // a (channel group, z, y) row of HX voxels = HX consecutive 16-byte chunks in smem, constant stride in HBM.
     unsigned slot = 0, slot_phase = 0;            // B ring cursor (issue side)
-    unsigned astage = 0, a_phase = 0;             // A double buffer cursor
+    unsigned astage = 0, a_phase = 0;             // A double buffer: stage/phase of the NEXT halo to be loaded
     unsigned done_slot = 0;                       // completion cursor (LAG items behind)
     int pending = 0;
-    for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
+    const int my_tiles = (tl.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_chunks = my_tiles * KC;
+    constexpr int HROWS = KG * HALO_SLICES * HY;
+
+    auto load_halo = [&](int chunk) {
+      const int tile = blockIdx.x + (chunk / KC) * gridDim.x;
+      const int kc = chunk % KC;
       int n, d0, h0, w0, nt;
       decode_tile(tile, n, d0, h0, w0, nt);
-      const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin;
-      for (int kc = 0; kc < KC; ++kc) {
-        for (int t = 0; t < T; ++t) {
-          mbar_wait(EMPTYB(slot), slot_phase ^ 1);
-          if (t == 0) {
-            mbar_wait(EMPTYA(astage), a_phase ^ 1);
-            const unsigned a_base = smem_u32(sA + astage * A_BYTES);
-            for (int i = tid; i < KG * HV; i += NUM_PROD) {
-              const int gidx = i / HV; int r = i - gidx * HV;
-              const int z = r / (HY * HX); r -= z * (HY * HX);
-              const int y = r / HX; const int x = r - y * HX;
-              const int d = d0 - 1 + z, h = h0 - 1 + y, w = w0 - 1 + x;
-              const bool ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi && (unsigned)w < (unsigned)g.Wi;
-              const __nv_bfloat16* src = ok ? in_n + ((size_t)(d * g.Hi + h) * g.Wi + w) * g.Cin + kc * 32 + gidx * 8 : in;
-              cp_async16(a_base + i * 16, src, ok);
-            }
-          }
-          {
-            const unsigned b_base = smem_u32(sB + slot * B_BYTES);
-            const __nv_bfloat16* wsrc = wgt + ((size_t)g.tap_w[t] * ep.CoutPad + nt * N_TILE) * g.Cin + kc * 32;
-            for (int i = tid; i < N_TILE * KG; i += NUM_PROD) {
-              const int kg = i / N_TILE, nr = i - kg * N_TILE;
-              cp_async16(b_base + i * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
-            }
-          }
-          cp_async_commit();
-          ++pending;
-          if (pending > LAG) {
-            cp_async_wait<LAG>();
-            fence_proxy_async();
-            mbar_arrive(FULLB(done_slot));
-            done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
-            --pending;
-          }
-          if (t == T - 1) { astage ^= 1; if (astage == 0) a_phase ^= 1; }
-          if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
+      if (!mbar_test(EMPTYA(astage), a_phase ^ 1)) {
+        // The halo buffer is still being read.  Its release needs the MMAs of the previous chunk, which may be
+        // waiting for weight items whose (deferred) arrival this thread still owes: publish them before blocking.
+        cp_async_wait<0>();
+        fence_proxy_async();
+        while (pending > 0) {
+          mbar_arrive(FULLB(done_slot));
+          done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
+          --pending;
         }
+        mbar_wait(EMPTYA(astage), a_phase ^ 1);
+      }
+      const unsigned a_base = smem_u32(sA + astage * A_BYTES);
+      const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin + kc * 32;
+      for (int rr = tid; rr < HROWS; rr += NUM_PROD) {
+        const int gidx = rr / (HALO_SLICES * HY); const int r2 = rr - gidx * (HALO_SLICES * HY);
+        const int z = r2 / HY, y = r2 - z * HY;
+        const int d = d0 - 1 + z, h = h0 - 1 + y;
+        const bool row_ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
+        const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + (w0 - 1)) * g.Cin + gidx * 8;
+        unsigned dst = a_base + rr * (HX * 16);
+#pragma unroll
+        for (int x = 0; x < HX; ++x) {
+          const bool ok = row_ok && (unsigned)(w0 - 1 + x) < (unsigned)g.Wi;
+          cp_async16(dst, ok ? src : in, ok);
+          dst += 16; src += g.Cin;
+        }
+      }
+      astage ^= 1; if (astage == 0) a_phase ^= 1;
+    };
+
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int tile = blockIdx.x + (chunk / KC) * gridDim.x;
+      const int kc = chunk % KC;
+      const int nt = tile % tl.NT;
+      const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * 32;
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(EMPTYB(slot), slot_phase ^ 1);
+        if (chunk == 0 && t == 0) load_halo(0);
+        if (t == T / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
+        {
+          const unsigned b_base = smem_u32(sB + slot * B_BYTES);
+          const __nv_bfloat16* wsrc = wbase + (size_t)g.tap_w[t] * ep.CoutPad * g.Cin;
+          for (int i = tid; i < N_TILE * KG; i += NUM_PROD) {
+            const int kg = i / N_TILE, nr = i - kg * N_TILE;
+            cp_async16(b_base + i * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
+          }
+        }
+        cp_async_commit();
+        ++pending;
+        if (pending > LAG) {
+          cp_async_wait<LAG>();
+          fence_proxy_async();
+          mbar_arrive(FULLB(done_slot));
+          done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
+          --pending;
+        }
+        if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
     }
     cp_async_wait<0>();
@@ -213,30 +253,27 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
       --pending;
     }
-  } else if (warp == 4) {
-    // ================================================================ MMA issuer
+  } else if (warp < 4 + MT) {
+    // ================================================================ MMA issuers: one warp (lane 0) per depth slice.
+    // The MT slices accumulate into disjoint TMEM columns, so their MMA streams are independent; a single thread
+    // cannot issue the 16..64-cycle MMAs of this kernel fast enough (~80 issue cycles each), MT threads can.
     if (lane == 0) {
+      const int mt = warp - 4;
       unsigned slot = 0, slot_phase = 0, astage = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
         mbar_wait(TEMPTY(acc), acc_phase ^ 1);
         tc_fence_after();
-        const unsigned d_tmem = tmem_base + acc * ACC_COLS;
+        const unsigned d_tmem = tmem_base + acc * ACC_COLS + mt * N_TILE;
         for (int kc = 0; kc < KC; ++kc) {
-          const unsigned a_base = smem_u32(sA + astage * A_BYTES);
+          // only the 14-bit start-address field changes between MMAs: add (byte offset >> 4) to a base descriptor
+          const unsigned long long a_desc0 = make_desc(smem_u32(sA + astage * A_BYTES) + mt * SLICE_PITCH, LBO_A, SBO_A);
           for (int t = 0; t < T; ++t) {
             mbar_wait(FULLB(slot), slot_phase);
             tc_fence_after();
-            const unsigned b_base = smem_u32(sB + slot * B_BYTES);
-            const unsigned a_tap = a_base + (unsigned)s_tapoff[t];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-              for (int k16 = 0; k16 < 2; ++k16) {
-                const unsigned long long ad = make_desc(a_tap + mt * SLICE_PITCH + k16 * 2 * LBO_A, LBO_A, SBO_A);
-                const unsigned long long bd = make_desc(b_base + k16 * 2 * LBO_B, LBO_B, SBO_B);
-                tc_mma(d_tmem + mt * N_TILE, ad, bd, IDESC, (kc | t | k16) != 0 ? 1u : 0u);
-              }
-            }
+            const unsigned long long b_desc0 = make_desc(smem_u32(sB + slot * B_BYTES), LBO_B, SBO_B);
+            const unsigned long long a_tap = a_desc0 + (unsigned long long)(s_tapoff[t] >> 4);
+            tc_mma(d_tmem, a_tap, b_desc0, IDESC, (kc | t) != 0 ? 1u : 0u);
+            tc_mma(d_tmem, a_tap + (unsigned long long)((2 * LBO_A) >> 4), b_desc0 + (unsigned long long)((2 * LBO_B) >> 4), IDESC, 1u);
             tc_commit(EMPTYB(slot));
             if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
           }
@@ -248,7 +285,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       }
     }
   } else {
-    // ================================================================ epilogue (warps 5..8 -> TMEM lane quarter warp % 4)
+    // ================================================================ epilogue (4 warps -> TMEM lane quarter warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // MMA row = TMEM lane = voxel (hy, wx) of a slice
     const int hy = row >> 3, wx = row & 7;
@@ -330,7 +367,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
 #pragma unroll
         for (int c = 0; c < N_TILE / 32; ++c) { s_stat[0][q][c * 32 + stat_col] = ssum[c]; s_stat[1][q][c * 32 + stat_col] = ssq[c]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int et = tid - 5 * 32;               // 0..127
+        const int et = tid - (4 + MT) * 32;        // 0..127
         for (int ch = et; ch < N_TILE; ch += 128) {
           const float s = s_stat[0][0][ch] + s_stat[0][1][ch] + s_stat[0][2][ch] + s_stat[0][3][ch];
           const float qq = s_stat[1][0][ch] + s_stat[1][1][ch] + s_stat[1][2][ch] + s_stat[1][3][ch];
@@ -363,7 +400,7 @@ int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g
     attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
-  conv_tc_kernel<N_TILE, MT><<<grid, TC_THREADS, smem, st>>>(in, w, g, ep, tl);
+  conv_tc_kernel<N_TILE, MT><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
   NND_LAUNCH_CHECK("conv_tc_kernel");
   return NND_OK;
 }

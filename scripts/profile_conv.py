@@ -1,0 +1,32 @@
+"""Run single conv layers in isolation (for `ncu --set full -k regex:conv_`): python scripts/profile_conv.py [cin cout size batch]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nndetection_b200.arch import conv_ops as ops
+from nndetection_b200.arch.conv import ConvInstanceRelu
+
+cin, cout, size, bs = (int(a) for a in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 32, 128, 4)))
+mode = sys.argv[5] if len(sys.argv) > 5 else "fprop"
+dev = torch.device("cuda")
+layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
+x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+plan = layer.plan(bs, (size,) * 3)
+wp, wb = layer.packed()
+y = ops.empty_cl(bs, cout, plan.out_sp, device=dev)
+st = torch.zeros((2, bs, cout), dtype=torch.float32, device=dev)
+dw = torch.zeros_like(layer.conv.weight)
+def run():
+    if mode == "fprop":
+        return ops.conv_gather(x, wp, plan.fprop[0], y, cout, cout, stat_sum=st[0], stat_sq=st[1])
+    ops.conv_wgrad(y, cout, x, cin, plan.wgrad[0], dw, cin * 27, 27, 1, cout, cin)
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    run()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+fl = 2.0 * 27 * cin * cout * bs * size ** 3
+print(f"{mode} {cin}->{cout} @{size}^3 x{bs}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
