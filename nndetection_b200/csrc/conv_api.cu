@@ -9,6 +9,9 @@ int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom&
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_wgrad(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                    long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_wgrad_halo_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                        long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_first_fprop(const float* x, const float* w, const ConvGeom& g, int Cout, __nv_bfloat16* out, float* stat_sum,
                          float* stat_sq, cudaStream_t st);
 int nnd_conv_first_wgrad(const float* x, const __nv_bfloat16* dy, const ConvGeom& g, int Cout, float* dw, cudaStream_t st);
@@ -56,6 +59,8 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx))
+    return nnd_conv_wgrad_halo((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   return nnd_conv_wgrad((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
 }
 
