@@ -38,6 +38,23 @@ class _HeadLossFn(torch.autograd.Function):
         return d_logits, d_deltas, None, None, None, None, None, None
 
 
+class DeferredPrediction:
+    """Detections of a train step whose per-image counts have not been read back yet.  `resolve()` performs the one
+    host read and returns the reference's prediction dict (lists of [R, ...] tensors)."""
+
+    def __init__(self, ob, os_, ol, oc, pred_seg):
+        self.ob, self.os_, self.ol, self.oc, self.pred_seg = ob, os_, ol, oc, pred_seg
+
+    def resolve(self) -> Dict[str, Any]:
+        cnt = self.oc.tolist()
+        out = {"pred_boxes": [self.ob[i, :c] for i, c in enumerate(cnt)],
+               "pred_scores": [self.os_[i, :c] for i, c in enumerate(cnt)],
+               "pred_labels": [self.ol[i, :c] for i, c in enumerate(cnt)]}
+        if self.pred_seg is not None:
+            out["pred_seg"] = self.pred_seg
+        return out
+
+
 class BaseRetinaNet(nn.Module):
     def __init__(self, dim: int, encoder, decoder, head, num_classes: int, anchor_generator, matcher,
                  decoder_levels: tuple = (2, 3, 4, 5), score_thresh: float = None, detections_per_img: int = 100,
@@ -54,6 +71,9 @@ class BaseRetinaNet(nn.Module):
         self.score_thresh, self.topk_candidates = score_thresh, topk_candidates
         self.detections_per_img, self.remove_small_boxes, self.nms_thresh = detections_per_img, remove_small_boxes, nms_thresh
         self.segmenter = segmenter
+        # True: train_step(evaluation=True) returns a DeferredPrediction so that the caller can enqueue backward and
+        # the optimizer before the (only) host synchronisation of the step (nndetection_b200.training.Trainer does).
+        self.defer_prediction_sync = False
 
     # ---------------------------------------------------------------- forward (retina.py:198-226)
     def forward(self, inp: Tensor):
@@ -92,8 +112,15 @@ class BaseRetinaNet(nn.Module):
 
         prediction = None
         if evaluation:
-            prediction = self.postprocess_for_inference(images=images, pred_detection=pred_detection,
-                                                        pred_seg=pred_seg, anchors=anchors)
+            if self.defer_prediction_sync:
+                with torch.no_grad():
+                    det = {k: v.detach() for k, v in pred_detection.items()}
+                    ob, os_, ol, oc = self.postprocess_detections_device(det, anchors, images.shape[2:])
+                    seg = self.segmenter.postprocess_for_inference(pred_seg)["pred_seg"] if self.segmenter is not None else None
+                prediction = DeferredPrediction(ob, os_, ol, oc, seg)
+            else:
+                prediction = self.postprocess_for_inference(images=images, pred_detection=pred_detection,
+                                                            pred_seg=pred_seg, anchors=anchors)
         return losses, prediction
 
     @torch.no_grad()

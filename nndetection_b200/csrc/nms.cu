@@ -137,9 +137,17 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long rem = remv[b], km = 0ull;
-#pragma unroll 16
-      for (int j = 0; j < TILE; ++j) {
-        if (j < cnt && !((rem >> j) & 1ull)) { km |= 1ull << j; rem |= s_diag[j]; }
+#pragma unroll
+      for (int j0 = 0; j0 < TILE; j0 += 16) {
+        unsigned long long dg[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) dg[u] = s_diag[j0 + u];          // independent loads, then a register-only chain
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const bool take = (j0 + u < cnt) && !((rem >> (j0 + u)) & 1ull);
+          km |= take ? (1ull << (j0 + u)) : 0ull;
+          rem |= take ? dg[u] : 0ull;
+        }
       }
       s_kmask = km;
     }
@@ -151,20 +159,20 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       keep_out[pos] = (long long)order[base + threadIdx.x];
     }
     // OR the mask rows of this block's kept boxes into remv[c], c > b.  Loads are independent: issue them in
-    // batches of 8 so the L2/HBM latency is paid once per batch, not once per kept row.
+    // batches of 16 so the L2/HBM latency is paid once per batch, not once per kept row.
     for (int c = b + 1 + threadIdx.x; c < col_blocks; c += blockDim.x) {
       unsigned long long acc = remv[c], m = km;
       const unsigned long long* col = mask + (size_t)base * col_blocks + c;
       while (m) {
-        unsigned long long v[8];
+        unsigned long long v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int j = m ? __ffsll((long long)m) - 1 : -1;
           m &= m - 1;                                    // 0 stays 0
           v[u] = j >= 0 ? __ldg(col + (size_t)j * col_blocks) : 0ull;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc |= v[u];
+        for (int u = 0; u < 16; ++u) acc |= v[u];
       }
       remv[c] = acc;
     }

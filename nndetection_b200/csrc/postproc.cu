@@ -155,6 +155,22 @@ struct PostWs {
   void* cub_tmp; size_t cub_bytes; void* nms_ws; size_t nms_bytes; size_t total;
 };
 
+constexpr int MAX_POST_STREAMS = 8;
+cudaStream_t g_streams[MAX_POST_STREAMS];
+cudaEvent_t g_fork, g_join[MAX_POST_STREAMS];
+bool g_streams_ready = false;
+
+int ensure_streams() {
+  if (g_streams_ready) return NND_OK;
+  for (int i = 0; i < MAX_POST_STREAMS; ++i) {
+    NND_CUDA_TRY(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
+    NND_CUDA_TRY(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+  }
+  NND_CUDA_TRY(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+  g_streams_ready = true;
+  return NND_OK;
+}
+
 PostWs carve(void* ws, int k) {
   PostWs w;
   char* p = reinterpret_cast<char*>(ws);
@@ -188,7 +204,7 @@ extern "C" {
 size_t nnd_detect_postprocess_workspace_bytes(long long A, int C, int topk) {
   long long k = topk < A ? topk : A;
   if (k <= 0) return 256;
-  return carve(nullptr, (int)k).total;
+  return carve(nullptr, (int)k).total * MAX_POST_STREAMS;     // one private workspace per concurrent image
 }
 
 // boxes [B*A,6] decoded + clipped; probs [B*A*C]; out_* sized [B, det_per_img, ...]; out_counts [B] (device).
@@ -200,34 +216,46 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
   if (!boxes || !probs || !out_boxes || !out_scores || !out_labels || !out_counts || !ws) return NND_ERR_ARG;
   if (A * C > 0xFFFFFFFFll) return NND_ERR_ARG;
   const int k = (int)(topk < A ? topk : A);
-  PostWs w = carve(ws, k);
-  if (w.total > ws_bytes) return NND_ERR_WORKSPACE;
+  const size_t per = carve(nullptr, k).total;
+  if (per * MAX_POST_STREAMS > ws_bytes) return NND_ERR_WORKSPACE;
   const long long n = A * C;
   NND_CUDA_TRY(cudaMemsetAsync(out_counts, 0, sizeof(int) * B, st));
+  // The per-image chains are dominated by single-CTA kernels (ordered filter, NMS scan): run the images of a batch
+  // concurrently on forked streams (each with its own workspace slice), then join back into the caller's stream.
+  int rc = ensure_streams();
+  if (rc != NND_OK) return rc;
+  NND_CUDA_TRY(cudaEventRecord(g_fork, st));
   const int hist_blocks = (int)((n + 511) / 512 < NND_NUM_SMS * 4 ? (n + 511) / 512 : NND_NUM_SMS * 4);
   for (int b = 0; b < B; ++b) {
+    const int si = b % MAX_POST_STREAMS;
+    cudaStream_t s = g_streams[si];
+    if (b < MAX_POST_STREAMS) NND_CUDA_TRY(cudaStreamWaitEvent(s, g_fork, 0));
+    PostWs w = carve(reinterpret_cast<char*>(ws) + per * si, k);
     const float* pv = probs + (size_t)b * n;
-    topk_init_kernel<<<1, 256, 0, st>>>(w.st, w.ghist, w.counter, k, n);
+    topk_init_kernel<<<1, 256, 0, s>>>(w.st, w.ghist, w.counter, k, n);
     NND_LAUNCH_CHECK("topk_init_kernel");
     for (int round = 0; round < 8; ++round) {
-      pool_hist_kernel<<<hist_blocks, 512, 0, st>>>(nullptr, pv, n, w.st, w.ghist);
-      pool_pick_kernel<<<1, 256, 0, st>>>(w.st, w.ghist);
+      pool_hist_kernel<<<hist_blocks, 512, 0, s>>>(nullptr, pv, n, w.st, w.ghist);
+      pool_pick_kernel<<<1, 256, 0, s>>>(w.st, w.ghist);
     }
     NND_LAUNCH_CHECK("topk select");
-    topk_collect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pv, n, w.st, k, w.keys, w.counter);
+    topk_collect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pv, n, w.st, k, w.keys, w.counter);
     NND_LAUNCH_CHECK("topk_collect_kernel");
     size_t cb = w.cub_bytes;
-    NND_CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(w.cub_tmp, cb, w.keys, w.keys_sorted, k, 0, 64, st));
-    post_filter_kernel<<<1, 1024, 0, st>>>(w.keys_sorted, k, boxes + (size_t)b * A * 6, C, score_thresh,
-                                           use_score_thresh, min_size, use_min_size, w.cand_boxes, w.nms_boxes,
-                                           w.scores, w.labels, w.m);
+    NND_CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(w.cub_tmp, cb, w.keys, w.keys_sorted, k, 0, 64, s));
+    post_filter_kernel<<<1, 1024, 0, s>>>(w.keys_sorted, k, boxes + (size_t)b * A * 6, C, score_thresh, use_score_thresh,
+                                          min_size, use_min_size, w.cand_boxes, w.nms_boxes, w.scores, w.labels, w.m);
     NND_LAUNCH_CHECK("post_filter_kernel");
-    int rc = nnd_nms3d_f32(w.nms_boxes, w.scores, k, nms_thresh, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, st);
+    rc = nnd_nms3d_f32(w.nms_boxes, w.scores, k, nms_thresh, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, s);
     if (rc != NND_OK) return rc;
-    post_gather_kernel<<<1, 128, 0, st>>>(w.keep, w.n_keep, w.m, w.cand_boxes, w.scores, w.labels, det_per_img,
-                                          out_boxes + (size_t)b * det_per_img * 6, out_scores + (size_t)b * det_per_img,
-                                          out_labels + (size_t)b * det_per_img, out_counts + b);
+    post_gather_kernel<<<1, 128, 0, s>>>(w.keep, w.n_keep, w.m, w.cand_boxes, w.scores, w.labels, det_per_img,
+                                         out_boxes + (size_t)b * det_per_img * 6, out_scores + (size_t)b * det_per_img,
+                                         out_labels + (size_t)b * det_per_img, out_counts + b);
     NND_LAUNCH_CHECK("post_gather_kernel");
+  }
+  for (int i = 0; i < (B < MAX_POST_STREAMS ? B : MAX_POST_STREAMS); ++i) {
+    NND_CUDA_TRY(cudaEventRecord(g_join[i], g_streams[i]));
+    NND_CUDA_TRY(cudaStreamWaitEvent(st, g_join[i], 0));
   }
   return NND_OK;
 }

@@ -91,10 +91,13 @@ class Trainer:
     def train_step(self, images: torch.Tensor, targets: dict, evaluation: bool = False):
         self.model.train()
         self.fp.zero_grad()
+        self.model.defer_prediction_sync = True
         losses, prediction = self.model.train_step(images, targets, evaluation=evaluation, batch_num=self.step_idx)
         loss = sum(losses.values())
         loss.backward()
         if self.distributed:
             dist.all_reduce(self.fp.grad)      # 76 MB fp32, NCCL over NVLink; mean folded into the SGD kernel
         self.optimizer_step()
+        if prediction is not None:
+            prediction = prediction.resolve()      # the step's only host read, after everything is enqueued
         return losses, prediction
