@@ -26,7 +26,7 @@ constexpr int HY = BH + 2, HX = BW + 2;          // halo extents in h, w
 constexpr int ROW_PITCH = HX * 16;               // 160 B
 constexpr int SLICE_PITCH = HY * ROW_PITCH;      // 2880 B
 constexpr int KG = 4;                            // channel groups (of 8) per stage = 32 channels
-constexpr int A_STAGES = 2, B_SLOTS = 12, LAG = 6;
+constexpr int A_STAGES = 2;
 constexpr int NUM_PROD = 128;
 constexpr int tc_threads(int mt) { return (4 + mt + 4) * 32; }   // 4 producer + MT issuer + 4 epilogue warps
 
@@ -110,19 +110,22 @@ __device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane, int
   return v[0];
 }
 
-template <int N_TILE, int MT>
+// TG = taps per pipeline item (weight slices loaded / consumed together), ACC = TMEM accumulator stages
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS>
 __global__ void __launch_bounds__(tc_threads(MT), 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
                const ConvEpilogue ep, const TcTiles tl) {
   constexpr int HALO_SLICES = MT + 2;
   constexpr int HV = HALO_SLICES * HY * HX;                 // halo voxels per channel group
   constexpr int A_BYTES = KG * HV * 16;
-  constexpr int B_BYTES = N_TILE * KG * 16;
+  constexpr int B_TAP_BYTES = N_TILE * KG * 16;            // one tap slice [kg][n][8]
+  constexpr int B_BYTES = TG * B_TAP_BYTES;                 // one pipeline item
+  constexpr int LAG = B_SLOTS / 2;
   constexpr unsigned LBO_A = HV * 16, SBO_A = ROW_PITCH;
   constexpr unsigned LBO_B = N_TILE * 16, SBO_B = 128;
   constexpr int ACC_COLS = MT * N_TILE;                     // one accumulator stage
-  constexpr int TMEM_COLS = 2 * ACC_COLS >= 512 ? 512 : (2 * ACC_COLS >= 256 ? 256 : (2 * ACC_COLS >= 128 ? 128 : 64));
-  static_assert(2 * ACC_COLS <= 512, "TMEM overflow");
+  constexpr int TMEM_COLS = ACC * ACC_COLS >= 512 ? 512 : (ACC * ACC_COLS >= 256 ? 256 : (ACC * ACC_COLS >= 128 ? 128 : 64));
+  static_assert(ACC * ACC_COLS <= 512, "TMEM overflow");
   constexpr unsigned IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N_TILE >> 3) << 17) | ((128u >> 4) << 24);
 
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -180,6 +183,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
     const int my_tiles = (tl.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_chunks = my_tiles * KC;
     constexpr int HROWS = KG * HALO_SLICES * HY;
+    const int NI_ITEMS = T / TG;
 
     auto load_halo = [&](int chunk) {
       const int tile = blockIdx.x + (chunk / KC) * gridDim.x;
@@ -222,15 +226,16 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const int kc = chunk % KC;
       const int nt = tile % tl.NT;
       const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * 32;
-      for (int t = 0; t < T; ++t) {
+      for (int it = 0; it < NI_ITEMS; ++it) {
         mbar_wait(EMPTYB(slot), slot_phase ^ 1);
-        if (chunk == 0 && t == 0) load_halo(0);
-        if (t == T / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
+        if (chunk == 0 && it == 0) load_halo(0);
+        if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
         {
           const unsigned b_base = smem_u32(sB + slot * B_BYTES);
-          const __nv_bfloat16* wsrc = wbase + (size_t)g.tap_w[t] * ep.CoutPad * g.Cin;
-          for (int i = tid; i < N_TILE * KG; i += NUM_PROD) {
-            const int kg = i / N_TILE, nr = i - kg * N_TILE;
+          for (int i = tid; i < TG * N_TILE * KG; i += NUM_PROD) {
+            const int tt = i / (N_TILE * KG); const int r = i - tt * (N_TILE * KG);
+            const int kg = r / N_TILE, nr = r - kg * N_TILE;
+            const __nv_bfloat16* wsrc = wbase + (size_t)g.tap_w[it * TG + tt] * ep.CoutPad * g.Cin;
             cp_async16(b_base + i * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
           }
         }
@@ -267,13 +272,17 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
         for (int kc = 0; kc < KC; ++kc) {
           // only the 14-bit start-address field changes between MMAs: add (byte offset >> 4) to a base descriptor
           const unsigned long long a_desc0 = make_desc(smem_u32(sA + astage * A_BYTES) + mt * SLICE_PITCH, LBO_A, SBO_A);
-          for (int t = 0; t < T; ++t) {
+          for (int it = 0; it < T / TG; ++it) {
             mbar_wait(FULLB(slot), slot_phase);
             tc_fence_after();
-            const unsigned long long b_desc0 = make_desc(smem_u32(sB + slot * B_BYTES), LBO_B, SBO_B);
-            const unsigned long long a_tap = a_desc0 + (unsigned long long)(s_tapoff[t] >> 4);
-            tc_mma(d_tmem, a_tap, b_desc0, IDESC, (kc | t) != 0 ? 1u : 0u);
-            tc_mma(d_tmem, a_tap + (unsigned long long)((2 * LBO_A) >> 4), b_desc0 + (unsigned long long)((2 * LBO_B) >> 4), IDESC, 1u);
+            const unsigned long long b_item = make_desc(smem_u32(sB + slot * B_BYTES), LBO_B, SBO_B);
+#pragma unroll
+            for (int tt = 0; tt < TG; ++tt) {
+              const unsigned long long b_desc0 = b_item + (unsigned long long)((tt * B_TAP_BYTES) >> 4);
+              const unsigned long long a_tap = a_desc0 + (unsigned long long)(s_tapoff[it * TG + tt] >> 4);
+              tc_mma(d_tmem, a_tap, b_desc0, IDESC, (kc | it | tt) != 0 ? 1u : 0u);
+              tc_mma(d_tmem, a_tap + (unsigned long long)((2 * LBO_A) >> 4), b_desc0 + (unsigned long long)((2 * LBO_B) >> 4), IDESC, 1u);
+            }
             tc_commit(EMPTYB(slot));
             if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
           }
@@ -281,7 +290,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
           astage ^= 1;
         }
         tc_commit(TFULL(acc));
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        if (ACC == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else acc_phase ^= 1;
       }
     }
   } else {
@@ -362,7 +371,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      if (ACC == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else acc_phase ^= 1;
       if (do_stats) {
 #pragma unroll
         for (int c = 0; c < N_TILE / 32; ++c) { s_stat[0][q][c * 32 + stat_col] = ssum[c]; s_stat[1][q][c * 32 + stat_col] = ssq[c]; }
@@ -387,20 +396,20 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   }
 }
 
-template <int N_TILE, int MT>
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS>
 int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   TcTiles tl;
   tl.DB = (g.Di + MT - 1) / MT; tl.HB = (g.Hi + BH - 1) / BH; tl.WB = (g.Wi + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
   tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
   constexpr int HV = (MT + 2) * HY * HX;
-  const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
+  const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
   static bool attr_set = false;
   if (!attr_set) {
-    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
-  conv_tc_kernel<N_TILE, MT><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
+  conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
   NND_LAUNCH_CHECK("conv_tc_kernel");
   return NND_OK;
 }
@@ -422,7 +431,14 @@ int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
 
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   if (!nnd_conv_tc_supported(g, ep)) return NND_ERR_ARG;
-  if (ep.Cout % 128 == 0) return launch_tc<128, 2>(in, w, g, ep, st);
-  if (ep.Cout % 64 == 0) return launch_tc<64, 4>(in, w, g, ep, st);
-  return launch_tc<32, 4>(in, w, g, ep, st);
+  const bool g3 = g.T % 3 == 0;          // taps come in (dz, dy) rows of three -> 3 taps per pipeline item
+  if (ep.Cout % 128 == 0) {
+    // 4 depth slices share each weight slice (halves the L2 weight traffic); small volumes keep 2-slice tiles so that
+    // the persistent grid still has >= one tile per SM
+    const long long tiles4 = (long long)g.N * ((g.Di + 3) / 4) * ((g.Hi + BH - 1) / BH) * ((g.Wi + BW - 1) / BW) * (ep.Cout / 128);
+    if (tiles4 >= NND_NUM_SMS) return launch_tc<128, 4, 1, 1, 6>(in, w, g, ep, st);
+    return launch_tc<128, 2, 1, 2, 12>(in, w, g, ep, st);
+  }
+  if (ep.Cout % 64 == 0) return g3 ? launch_tc<64, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<64, 4, 1, 2, 12>(in, w, g, ep, st);
+  return g3 ? launch_tc<32, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<32, 4, 1, 2, 12>(in, w, g, ep, st);
 }
