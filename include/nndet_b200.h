@@ -100,6 +100,7 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
  *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
  *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 1 if the tcgen05 kernel ran. */
 void nnd_conv_set_tensor_path(int enable_tcgen05);
+void nnd_conv_set_wgrad_tc(int enable);              /* A/B switch: tcgen05 wgrad (default) vs mma.sync halo wgrad */
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);

@@ -9,6 +9,9 @@ int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom&
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_wgrad(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                    long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                      long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_halo_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                         long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
@@ -33,12 +36,15 @@ int parse_geom(const int* a, ConvGeom& g) {
   return NND_OK;
 }
 int g_force_igemm = 0;
+int g_wgrad_tc = 1;
 }  // namespace
 
 extern "C" {
 
 // 1: route eligible layers to the tcgen05 kernel (default), 0: always use the mma.sync kernel (cross-check / debugging)
 void nnd_conv_set_tensor_path(int enable_tcgen05) { g_force_igemm = !enable_tcgen05; }
+// 1 (default): tcgen05 wgrad where eligible; 0: mma.sync halo wgrad (A/B)
+void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
 
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
@@ -59,6 +65,8 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx))
+    return nnd_conv_wgrad_tc((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_halo((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   return nnd_conv_wgrad((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);

@@ -13,7 +13,7 @@
 namespace {
 
 constexpr int VB_H = 8, VB_W = 16;                 // voxel block 1 x 8 x 16 (K = 128 voxels = 8 k16 steps)
-constexpr int HB_H = VB_H + 2, HB_W = VB_W + 2;    // halo extents
+// halo extents depend on the stride: rows (VB_H - 1) * sh + 3, columns (VB_W - 1) * sw + 3  (10 x 18 at stride 1, 17 x 33 at 2)
 
 template <int ROWB>
 __device__ __forceinline__ int swzh(int row, int chunk) {
@@ -28,7 +28,10 @@ struct WhArgs {
   const __nv_bfloat16* x; int Cx;
   float* dw; long long s_co, s_ci, s_tap;
   int Cout, Cin;
-  int N, D, H, W;
+  int N, D, H, W;             // OUTPUT (dy) grid
+  int Di, Hi, Wi;             // input (x) grid
+  int sd, sh, sw;             // strides: x position = v * s + off
+  int hbh, hbw;               // halo rows / columns per depth slice
   int hb, wb;                 // blocks along h, w
   long long total_blocks;     // N * D * hb * wb
   long long blocks_per_split;
@@ -49,8 +52,10 @@ conv_wgrad_halo_kernel(const WhArgs a) {
   static_assert(BM == 16 * WM && (NI == 1 || NI == 2), "tile/warp mismatch");
   constexpr int THREADS = WM * WN * 32;
   constexpr int A_ROWB = BM * 2, B_ROWB = BN * 2;
-  constexpr int A_ROWS = VB_H * VB_W, B_ROWS = ZS * HB_H * HB_W;
-  constexpr int A_BYTES = A_ROWS * A_ROWB, B_BYTES = B_ROWS * B_ROWB;
+  constexpr int A_ROWS = VB_H * VB_W;
+  constexpr int A_BYTES = A_ROWS * A_ROWB;
+  const int HB_H = a.hbh, HB_W = a.hbw;
+  const int B_ROWS = ZS * HB_H * HB_W, B_BYTES = B_ROWS * B_ROWB;
   constexpr int A_CH = BM / 8, B_CH = BN / 8;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;                       // 2 stages
@@ -82,9 +87,9 @@ conv_wgrad_halo_kernel(const WhArgs a) {
     for (int i = tid; i < B_ROWS * B_CH; i += THREADS) {
       const int row = i / B_CH, ch = i % B_CH;
       const int zz = row / (HB_H * HB_W); const int r2 = row % (HB_H * HB_W);
-      const int dd = d + zbase + zz, h = h0 - 1 + r2 / HB_W, w = w0 - 1 + r2 % HB_W;
-      const bool ok = (unsigned)dd < (unsigned)a.D && (unsigned)h < (unsigned)a.H && (unsigned)w < (unsigned)a.W;
-      const __nv_bfloat16* src = ok ? a.x + ((((long long)n * a.D + dd) * a.H + h) * a.W + w) * a.Cx + ci0 + ch * 8 : a.x;
+      const int dd = d * a.sd + zbase + zz, h = h0 * a.sh - 1 + r2 / HB_W, w = w0 * a.sw - 1 + r2 % HB_W;
+      const bool ok = (unsigned)dd < (unsigned)a.Di && (unsigned)h < (unsigned)a.Hi && (unsigned)w < (unsigned)a.Wi;
+      const __nv_bfloat16* src = ok ? a.x + ((((long long)n * a.Di + dd) * a.Hi + h) * a.Wi + w) * a.Cx + ci0 + ch * 8 : a.x;
       cp_async16(b_base + row * B_ROWB + swzh<B_ROWB>(row, ch) * 16, src, ok);
     }
   };
@@ -126,9 +131,9 @@ conv_wgrad_halo_kernel(const WhArgs a) {
         const int mcol = warp_m * 16 + ((lane >> 3) & 1) * 8;
         ldmatrix_x4_trans(a_st + krow * A_ROWB + swzh<A_ROWB>(krow, mcol >> 3) * 16, af[0], af[1], af[2], af[3]);
       }
-      const int kk = (lane & 7) + ((lane >> 3) & 1) * 8;            // k index (w inside the block row) of this lane's row
+      const int kk = ((lane & 7) + ((lane >> 3) & 1) * 8) * a.sw;   // halo column of this lane's k index (w inside the block row)
       const int ncol = warp_n * (BN / WN) + (NI == 2 ? (lane >> 4) * 8 : 0);
-      const int row0 = hr * HB_W + kk;
+      const int row0 = hr * a.sh * HB_W + kk;
 #pragma unroll
       for (int t = 0; t < MAXT; ++t) {
         const int hv = toff[t] + row0;
@@ -164,7 +169,8 @@ conv_wgrad_halo_kernel(const WhArgs a) {
 template <int BM, int BN, int WM, int WN, int MAXT, int ZS>
 int launch_halo(WhArgs a, int co_pad, int ci_pad, cudaStream_t st) {
   constexpr int THREADS = WM * WN * 32;
-  constexpr size_t SMEM = 2 * ((size_t)VB_H * VB_W * BM * 2 + (size_t)ZS * HB_H * HB_W * BN * 2);
+  const size_t SMEM = 2 * ((size_t)VB_H * VB_W * BM * 2 + (size_t)ZS * a.hbh * a.hbw * BN * 2);
+  if (SMEM > 227 * 1024) return NND_ERR_ARG;
   const int co_tiles = co_pad / BM;
   a.ci_tiles = ci_pad / BN;
   const long long tiles = (long long)a.n_groups * co_tiles * a.ci_tiles;
@@ -173,10 +179,10 @@ int launch_halo(WhArgs a, int co_pad, int ci_pad, cudaStream_t st) {
   if (splits < 1) splits = 1;
   a.blocks_per_split = (a.total_blocks + splits - 1) / splits;
   splits = (a.total_blocks + a.blocks_per_split - 1) / a.blocks_per_split;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static size_t attr_smem = 0;
+  if (SMEM > attr_smem) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_halo_kernel<BM, BN, WM, WN, MAXT, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
+    attr_smem = SMEM;
   }
   dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(co_tiles * a.ci_tiles));
   conv_wgrad_halo_kernel<BM, BN, WM, WN, MAXT, ZS><<<grid, THREADS, SMEM, st>>>(a);
@@ -187,8 +193,9 @@ int launch_halo(WhArgs a, int co_pad, int ci_pad, cudaStream_t st) {
 }  // namespace
 
 int nnd_conv_wgrad_halo_supported(const ConvGeom& g, int Cdy, int Cx) {
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
-  if (g.Ld != g.Di || g.Lh != g.Hi || g.Lw != g.Wi || g.Do != g.Di || g.Ho != g.Hi || g.Wo != g.Wi) return 0;
+  if (g.sd < 1 || g.sd > 2 || g.sh < 1 || g.sh > 2 || g.sw < 1 || g.sw > 2) return 0;
+  if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
+  if (g.Ld != g.Do || g.Lh != g.Ho || g.Lw != g.Wo) return 0;
   if (g.T < 9 || Cdy % 32 || Cx % 32) return 0;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
@@ -199,11 +206,14 @@ int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x
                         long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
   WhArgs a;
   a.dy = dy; a.Cdy = Cdy; a.x = x; a.Cx = Cx; a.dw = dw; a.s_co = s_co; a.s_ci = s_ci; a.s_tap = s_tap;
-  a.Cout = Cout; a.Cin = Cin; a.N = g.N; a.D = g.Di; a.H = g.Hi; a.W = g.Wi;
-  a.hb = (g.Hi + VB_H - 1) / VB_H; a.wb = (g.Wi + VB_W - 1) / VB_W;
-  a.total_blocks = (long long)g.N * g.Di * a.hb * a.wb;
+  a.Cout = Cout; a.Cin = Cin; a.N = g.N; a.D = g.Do; a.H = g.Ho; a.W = g.Wo;
+  a.Di = g.Di; a.Hi = g.Hi; a.Wi = g.Wi; a.sd = g.sd; a.sh = g.sh; a.sw = g.sw;
+  a.hbh = (VB_H - 1) * g.sh + 3; a.hbw = (VB_W - 1) * g.sw + 3;
+  a.hb = (g.Ho + VB_H - 1) / VB_H; a.wb = (g.Wo + VB_W - 1) / VB_W;
+  a.total_blocks = (long long)g.N * g.Do * a.hb * a.wb;
   if (a.total_blocks <= 0) return NND_OK;
-  const bool small = (Cdy % 64 != 0) && (Cx % 64 != 0);       // 32 x 32 tiles: all taps in one CTA
+  const bool strided = g.sd != 1 || g.sh != 1 || g.sw != 1;
+  const bool small = (Cdy % 64 != 0) && (Cx % 64 != 0) && !strided;       // 32 x 32 tiles, stride 1: all taps in one CTA
   // order taps group by group (group = depth offset), or one group with everything
   int cnt = 0;
   a.n_groups = 0;
@@ -219,5 +229,6 @@ int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x
   if (m64 && n64) return launch_halo<64, 64, 4, 4, 9, 1>(a, Cdy, Cx, st);
   if (m64) return launch_halo<64, 32, 4, 2, 9, 1>(a, Cdy, Cx, st);
   if (n64) return launch_halo<32, 64, 2, 4, 9, 1>(a, Cdy, Cx, st);
-  return launch_halo<32, 32, 2, 4, 27, 3>(a, Cdy, Cx, st);
+  if (small) return launch_halo<32, 32, 2, 4, 27, 3>(a, Cdy, Cx, st);
+  return launch_halo<32, 32, 2, 4, 9, 1>(a, Cdy, Cx, st);
 }

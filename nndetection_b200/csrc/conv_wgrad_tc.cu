@@ -1,0 +1,308 @@
+// Weight gradient of 3x3x3 / 1x3x3 stride-1 convolutions on the 5th-generation tensor cores.
+//
+//   dW[tap][co][ci] = sum_voxels dy[v][co] * x[v + off_tap][ci]          (nndet/arch/conv.py:344-348 via autograd)
+//
+// As a UMMA: D[M = co][N = ci] += A[M][K] * B[N][K] with K = 16 consecutive voxels of one w-row.  Both operands live in
+// HBM as [voxel][channel] (NDHWC), i.e. they are "MN-major": staged in shared memory as [channel group of 8][row][voxel]
+// [8 ch] one voxel is again a 16-byte core-matrix row (canonical no-swizzle MN-major layout: 8 k-rows x 16 B, LBO =
+// 128 B between the two k-halves, SBO = channel-group pitch), and the three dx-taps of a filter row are the SAME x row
+// read at start offsets 0 / 16 / 32 bytes -- no im2col, no per-tap reload.
+// One CTA = one (dz, dy) filter row (3 taps -> 3 accumulators of N_T columns in TMEM), one 128-channel co tile, one
+// N_T-channel ci tile, one contiguous range of voxel rows (split-K).  4 producer warps (cp.async, zero fill = padding)
+// -> 4-stage ring -> 3 issuer warps (one per dx tap, independent accumulators) -> 4 epilogue warps (tcgen05.ld ->
+// fp32 atomicAdd into dW, PyTorch weight layout).
+#include "conv_common.cuh"
+
+namespace {
+
+constexpr int RW = 16;                 // voxels per row segment (K of one MMA)
+constexpr int XW = RW + 2;             // x row with halo
+constexpr int ROWS = 4;                // row segments per pipeline stage
+constexpr int STAGES = 4;
+constexpr int M_T = 128;               // co tile (UMMA M); channels beyond Cdy are zero rows
+constexpr int WG_THREADS = (4 + 3 + 4) * 32;
+constexpr int NPROD = 128;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                       unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ unsigned long long make_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+  return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct WtArgs {
+  const __nv_bfloat16* dy; int Cdy;
+  const __nv_bfloat16* x; int Cx;
+  float* dw; long long s_co, s_ci, s_tap;
+  int Cout, Cin;
+  int N, D, H, W, wsegs;            // grid and row segments per h-row (ceil(W / 16))
+  long long total_rows;             // N * D * H * wsegs
+  long long rows_per_split;
+  int n_groups;                     // filter rows (dz, dy)
+  signed char gdz[9], gdy[9];
+  unsigned char gtw[9][3];          // weight tap index of dx = -1, 0, +1 (255 = tap absent)
+  int ci_tiles;
+};
+
+template <int N_T>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tc_kernel(const WtArgs a) {
+  constexpr int A_GROUPS = M_T / 8, B_GROUPS = N_T / 8;
+  constexpr int A_GPITCH = ROWS * RW * 16;               // bytes between co groups inside a stage
+  constexpr int B_GPITCH = ROWS * XW * 16;               // bytes between ci groups
+  constexpr int A_BYTES = A_GROUPS * A_GPITCH, B_BYTES = B_GROUPS * B_GPITCH;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = 3 * N_T > 256 ? 512 : (3 * N_T > 128 ? 256 : 128);
+  // kind::f16, D fp32, A/B bf16, both MN-major (bits 15, 16), N >> 3 at 17, M >> 4 at 24
+  constexpr unsigned IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(N_T >> 3) << 17) | ((128u >> 4) << 24);
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + STAGES * STAGE_BYTES);
+  __shared__ unsigned s_tmem_base;
+  const unsigned bar0 = smem_u32(bars);
+  auto FULL = [&](int i) { return bar0 + 8u * i; };
+  auto EMPTY = [&](int i) { return bar0 + 8u * (STAGES + i); };
+  const unsigned DONE = bar0 + 8u * (2 * STAGES);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = blockIdx.y;
+  const int co0 = (blockIdx.z / a.ci_tiles) * M_T, ci0 = (blockIdx.z % a.ci_tiles) * N_T;
+  const long long r0 = (long long)blockIdx.x * a.rows_per_split;
+  const long long r1 = min(r0 + a.rows_per_split, a.total_rows);
+  const int n_stages = (int)((r1 - r0 + ROWS - 1) / ROWS);
+  const int dz = a.gdz[grp], dyo = a.gdy[grp];
+  const int co_groups = min(A_GROUPS, (a.Cdy - co0) / 8);           // real channel groups of this co tile
+
+  // zero the A region once: channel groups beyond Cdy stay zero for the whole kernel (zero MMA rows)
+  for (int i = tid; i < STAGES * STAGE_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(FULL(i), NPROD); mbar_init(EMPTY(i), 3); }
+    mbar_init(DONE, 3);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = s_tmem_base;
+  if (n_stages > 0) {
+  if (warp < 4) {
+    // ================================================================ producers
+    unsigned stage = 0, phase = 0;
+    int pending = 0; unsigned done_stage = 0;
+    constexpr int LAGW = 2;
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_wait(EMPTY(stage), phase ^ 1);
+      const unsigned sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+      // A: dy rows  [co group][row][16 voxels]   B: x rows [ci group][row][18 voxels]
+      const int a_items = co_groups * ROWS, b_items = B_GROUPS * ROWS;
+      for (int it = tid; it < a_items + b_items; it += NPROD) {
+        const bool isA = it < a_items;
+        const int j = isA ? it : it - a_items;
+        const int gidx = j / ROWS, rr = j % ROWS;
+        const long long row = r0 + (long long)s * ROWS + rr;
+        bool row_ok = row < r1;
+        int ws = 0, h = 0, d = 0, n = 0;
+        if (row_ok) { ws = (int)(row % a.wsegs); long long q = row / a.wsegs; h = (int)(q % a.H); q /= a.H; d = (int)(q % a.D); n = (int)(q / a.D); }
+        if (isA) {
+          const __nv_bfloat16* src = a.dy + ((((long long)n * a.D + d) * a.H + h) * a.W + ws * RW) * a.Cdy + co0 + gidx * 8;
+          unsigned dst = sa + gidx * A_GPITCH + rr * (RW * 16);
+#pragma unroll
+          for (int v = 0; v < RW; ++v) {
+            const bool ok = row_ok && ws * RW + v < a.W;
+            cp_async16(dst, ok ? src : a.dy, ok);
+            dst += 16; src += a.Cdy;
+          }
+        } else {
+          const int dd = d + dz, hh = h + dyo;
+          row_ok = row_ok && (unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H;
+          const __nv_bfloat16* src = a.x + ((((long long)n * a.D + dd) * a.H + hh) * a.W + (ws * RW - 1)) * a.Cx + ci0 + gidx * 8;
+          unsigned dst = sb + gidx * B_GPITCH + rr * (XW * 16);
+#pragma unroll
+          for (int v = 0; v < XW; ++v) {
+            const bool ok = row_ok && (unsigned)(ws * RW - 1 + v) < (unsigned)a.W;
+            cp_async16(dst, ok ? src : a.x, ok);
+            dst += 16; src += a.Cx;
+          }
+        }
+      }
+      cp_async_commit();
+      ++pending;
+      if (pending > LAGW) {
+        cp_async_wait<LAGW>();
+        fence_proxy_async();
+        mbar_arrive(FULL(done_stage));
+        done_stage = (done_stage + 1 == STAGES) ? 0 : done_stage + 1;
+        --pending;
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    while (pending > 0) {
+      mbar_arrive(FULL(done_stage));
+      done_stage = (done_stage + 1 == STAGES) ? 0 : done_stage + 1;
+      --pending;
+    }
+  } else if (warp < 7) {
+    // ================================================================ MMA issuers: one per dx tap
+    if (lane == 0) {
+      const int tap = warp - 4;                       // dx = tap - 1 -> x start offset tap * 16 bytes
+      const bool present = a.gtw[grp][tap] != 255;
+      unsigned stage = 0, phase = 0;
+      const unsigned d_tmem = tmem_base + tap * N_T;
+      for (int s = 0; s < n_stages; ++s) {
+        mbar_wait(FULL(stage), phase);
+        tc_fence_after();
+        if (present) {
+          const unsigned sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
+          const unsigned long long a0 = make_desc(sa, 128, A_GPITCH);
+          const unsigned long long b0 = make_desc(sb + tap * 16, 128, B_GPITCH);
+#pragma unroll
+          for (int rr = 0; rr < ROWS; ++rr)
+            tc_mma(d_tmem, a0 + (unsigned long long)((rr * RW * 16) >> 4), b0 + (unsigned long long)((rr * XW * 16) >> 4), IDESC,
+                   (s | rr) != 0 ? 1u : 0u);
+        }
+        tc_commit(EMPTY(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(DONE);
+    }
+  } else {
+    // ================================================================ epilogue: TMEM -> fp32 atomics into dW
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    mbar_wait(DONE, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int tap = 0; tap < 3; ++tap) {
+      const int tw = a.gtw[grp][tap];
+      if (tw == 255) continue;
+      float* dwt = a.dw + (long long)tw * a.s_tap + (long long)co * a.s_co;
+#pragma unroll 1
+      for (int c = 0; c < N_T / 32; ++c) {
+        unsigned v[32];
+        tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + tap * N_T + c * 32, v);
+        if (co < a.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ci = ci0 + c * 32 + j;
+            if (ci < a.Cin) atomicAdd(dwt + (long long)ci * a.s_ci, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+template <int N_T>
+int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
+  const int co_tiles = (co_pad + M_T - 1) / M_T;
+  a.ci_tiles = ci_pad / N_T;
+  const long long tiles = (long long)a.n_groups * co_tiles * a.ci_tiles;
+  long long splits = NND_NUM_SMS / tiles;            // one wave of 1-CTA-per-SM blocks
+  const long long max_splits = (a.total_rows + 4 * ROWS - 1) / (4 * ROWS);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.rows_per_split = (a.total_rows + splits - 1) / splits;
+  a.rows_per_split = (a.rows_per_split + ROWS - 1) / ROWS * ROWS;
+  splits = (a.total_rows + a.rows_per_split - 1) / a.rows_per_split;
+  constexpr size_t SMEM = (size_t)STAGES * ((M_T / 8) * ROWS * RW * 16 + (N_T / 8) * ROWS * XW * 16) + 8 * (2 * STAGES + 1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<N_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(co_tiles * a.ci_tiles));
+  conv_wgrad_tc_kernel<N_T><<<grid, WG_THREADS, SMEM, st>>>(a);
+  NND_LAUNCH_CHECK("conv_wgrad_tc_kernel");
+  return NND_OK;
+}
+
+}  // namespace
+
+int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx) {
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
+  if (g.Ld != g.Di || g.Lh != g.Hi || g.Lw != g.Wi || g.Do != g.Di || g.Ho != g.Hi || g.Wo != g.Wi) return 0;
+  if (g.T < 9 || Cdy % 32 || Cx % 32 || Cdy < 64) return 0;        // 32-channel dy would fill a quarter of the 128-row MMA
+  for (int t = 0; t < g.T; ++t)
+    if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
+  return 1;
+}
+
+int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                      long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
+  WtArgs a;
+  a.dy = dy; a.Cdy = Cdy; a.x = x; a.Cx = Cx; a.dw = dw; a.s_co = s_co; a.s_ci = s_ci; a.s_tap = s_tap;
+  a.Cout = Cout; a.Cin = Cin; a.N = g.N; a.D = g.Di; a.H = g.Hi; a.W = g.Wi;
+  a.wsegs = (g.Wi + RW - 1) / RW;
+  a.total_rows = (long long)g.N * g.Di * g.Hi * a.wsegs;
+  if (a.total_rows <= 0) return NND_OK;
+  a.n_groups = 0;
+  for (int z = -1; z <= 1; ++z)
+    for (int y = -1; y <= 1; ++y) {
+      int found = 0;
+      unsigned char tw[3] = {255, 255, 255};
+      for (int t = 0; t < g.T; ++t)
+        if (g.off_d[t] == z && g.off_h[t] == y) { tw[g.off_w[t] + 1] = g.tap_w[t]; found = 1; }
+      if (found) {
+        a.gdz[a.n_groups] = (signed char)z; a.gdy[a.n_groups] = (signed char)y;
+        for (int k = 0; k < 3; ++k) a.gtw[a.n_groups][k] = tw[k];
+        ++a.n_groups;
+      }
+    }
+  if (Cx % 128 == 0) return launch_wt<128>(a, Cdy, Cx, st);
+  if (Cx % 64 == 0) return launch_wt<64>(a, Cdy, Cx, st);
+  return launch_wt<32>(a, Cdy, Cx, st);
+}

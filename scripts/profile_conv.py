@@ -7,6 +7,10 @@ from nndetection_b200.arch.conv import ConvInstanceRelu
 
 cin, cout, size, bs = (int(a) for a in (sys.argv[1:5] if len(sys.argv) >= 5 else (32, 32, 128, 4)))
 mode = sys.argv[5] if len(sys.argv) > 5 else "fprop"
+if len(sys.argv) > 6:
+    from nndetection_b200 import _lib as L
+    from ctypes import c_int
+    L.lib().nnd_conv_set_wgrad_tc(c_int(int(sys.argv[6])))
 dev = torch.device("cuda")
 layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
 x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
