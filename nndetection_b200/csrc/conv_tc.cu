@@ -305,20 +305,21 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
     for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
       int n, d0, h0, w0, nt;
       decode_tile(tile, n, d0, h0, w0, nt);
-      const int h = h0 + hy, w = w0 + wx;
-      const bool hw_ok = h < g.Hi && w < g.Wi;
+      const int h = h0 + hy, w = w0 + wx;                    // logical output coordinates
+      const bool hw_ok = h < g.Lh && w < g.Lw;
       mbar_wait(TFULL(acc), acc_phase);
       tc_fence_after();
-      float ssum[N_TILE / 32], ssq[N_TILE / 32];
-#pragma unroll
-      for (int c = 0; c < N_TILE / 32; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
-      int stat_col = 0;
+      // per-warp rows of s_stat accumulate this tile's column sums (lane l owns column c*32 + l of its warp's row)
+      if (do_stats) {
+        for (int ch = lane; ch < N_TILE; ch += 32) { s_stat[0][q][ch] = 0.f; s_stat[1][q][ch] = 0.f; }
+      }
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int d = d0 + mt;
-        const bool ok = hw_ok && d < g.Di;
-        const long long vox = ((long long)(n * g.Di + d) * g.Hi + h) * g.Wi + w;
-#pragma unroll
+        const bool ok = hw_ok && d < g.Ld;
+        // physical voxel: lo * om + oo per axis (stride-2 dgrad writes one parity class of dx)
+        const long long vox = ((long long)(n * g.Do + d * g.omd + g.ood) * g.Ho + (h * g.omh + g.ooh)) * g.Wo + (w * g.omw + g.oow);
+#pragma unroll 1
         for (int c = 0; c < N_TILE / 32; ++c) {
           unsigned v[32];
           tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + acc * ACC_COLS + mt * N_TILE + c * 32, v);
@@ -328,7 +329,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (ep.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += ep.bias[co0 + j];
+            for (int j = 0; j < 32; ++j) if (co0 + j < ep.Cout) f[j] += ep.bias[co0 + j];
           }
           if (ep.residual && ok) {
             const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + vox * ep.Cout + co0);
@@ -343,27 +344,42 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= scale;
           __align__(16) __nv_bfloat162 pk[16];
+          if (!ep.out_fp32) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            pk[j] = __floats2bfloat162_rn(f[2 * j] * scale, f[2 * j + 1] * scale);
+            pk[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             const float2 r2 = __bfloat1622float2(pk[j]);
             f[2 * j] = ok ? r2.x : 0.f; f[2 * j + 1] = ok ? r2.y : 0.f;
           }
+          }
           if (ok) {
-            uint4* op = reinterpret_cast<uint4*>(outp + vox * ep.Cout + co0);
-            const uint4* sp = reinterpret_cast<const uint4*>(pk);
+            if (ep.out_fp32) {
+              // head outputs: fp32, written straight into the [N, anchors, C] layout (sample / voxel strides), channels
+              // beyond Cout are padding of the weight pack
+              const long long pv = vox - (long long)n * g.Do * g.Ho * g.Wo;
+              float* of = reinterpret_cast<float*>(ep.out) + (long long)n * ep.out_n_stride + pv * ep.out_v_stride + co0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) op[u] = sp[u];
+              for (int j = 0; j < 32; ++j)
+                if (co0 + j < ep.Cout) of[j] = f[j];
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(outp + vox * ep.Cout + co0);
+              const uint4* sp = reinterpret_cast<const uint4*>(pk);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) op[u] = sp[u];
+            }
           }
           if (do_stats) {
             float sq[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
             int col;
-            ssum[c] += warp_transpose_reduce32(f, lane, col);
-            ssq[c] += warp_transpose_reduce32(sq, lane, col);
-            stat_col = col;
+            const float cs = warp_transpose_reduce32(f, lane, col);
+            const float cq = warp_transpose_reduce32(sq, lane, col);
+            s_stat[0][q][c * 32 + col] += cs;          // col is a permutation of the lanes: no two lanes share a slot
+            s_stat[1][q][c * 32 + col] += cq;
           }
         }
       }
@@ -373,8 +389,6 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       if (lane == 0) mbar_arrive(TEMPTY(acc));
       if (ACC == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else acc_phase ^= 1;
       if (do_stats) {
-#pragma unroll
-        for (int c = 0; c < N_TILE / 32; ++c) { s_stat[0][q][c * 32 + stat_col] = ssum[c]; s_stat[1][q][c * 32 + stat_col] = ssq[c]; }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int et = tid - (4 + MT) * 32;        // 0..127
         for (int ch = et; ch < N_TILE; ch += 128) {
@@ -399,7 +413,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
 template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS>
 int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   TcTiles tl;
-  tl.DB = (g.Di + MT - 1) / MT; tl.HB = (g.Hi + BH - 1) / BH; tl.WB = (g.Wi + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
+  tl.DB = (g.Ld + MT - 1) / MT; tl.HB = (g.Lh + BH - 1) / BH; tl.WB = (g.Lw + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
   tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
   constexpr int HV = (MT + 2) * HY * HX;
   const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
@@ -417,28 +431,34 @@ int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g
 }  // namespace
 
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
-  if (g.sd != 1 || g.sh != 1 || g.sw != 1) return 0;
-  if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
-  if (g.Ld != g.Di || g.Lh != g.Hi || g.Lw != g.Wi || g.Do != g.Di || g.Ho != g.Hi || g.Wo != g.Wi) return 0;
-  if (g.T < 9 || g.Cin % 32) return 0;
+  if (g.sd != 1 || g.sh != 1 || g.sw != 1) return 0;                       // input position = logical position + offset
+  const bool identity = g.omd == 1 && g.omh == 1 && g.omw == 1 && !g.ood && !g.ooh && !g.oow;
+  if (identity && (g.Ld != g.Do || g.Lh != g.Ho || g.Lw != g.Wo)) return 0;
+  // 3x3x3 / 1x3x3 layers, or the >= 4-tap parity classes of a stride-2 dgrad (output = lo * 2 + parity)
+  if (!(g.T >= 9 || (!identity && g.T >= 4)) || g.Cin % 32) return 0;
+  if (ep.stat_sum && !identity) return 0;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
-  if (ep.out_fp32 || ep.Cout % 32 || ep.CoutPad != ep.Cout) return 0;
-  if (ep.out_v_stride != ep.Cout || ep.out_n_stride != (long long)g.Do * g.Ho * g.Wo * ep.Cout) return 0;
-  if (g.Hi < 8 || g.Wi < 8) return 0;
+  if (ep.out_fp32) {                       // strided fp32 head outputs: no residual / statistics, identity mapping
+    if (!identity || ep.residual || ep.stat_sum || ep.CoutPad % 32) return 0;
+  } else {
+    if (ep.Cout % 32 || ep.CoutPad != ep.Cout) return 0;
+    if (ep.out_v_stride != ep.Cout || ep.out_n_stride != (long long)g.Do * g.Ho * g.Wo * ep.Cout) return 0;
+  }
+  if (g.Lh < 8 || g.Lw < 8) return 0;
   return 1;
 }
 
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   if (!nnd_conv_tc_supported(g, ep)) return NND_ERR_ARG;
   const bool g3 = g.T % 3 == 0;          // taps come in (dz, dy) rows of three -> 3 taps per pipeline item
-  if (ep.Cout % 128 == 0) {
+  if (ep.CoutPad % 128 == 0) {
     // 4 depth slices share each weight slice (halves the L2 weight traffic); small volumes keep 2-slice tiles so that
     // the persistent grid still has >= one tile per SM
-    const long long tiles4 = (long long)g.N * ((g.Di + 3) / 4) * ((g.Hi + BH - 1) / BH) * ((g.Wi + BW - 1) / BW) * (ep.Cout / 128);
+    const long long tiles4 = (long long)g.N * ((g.Ld + 3) / 4) * ((g.Lh + BH - 1) / BH) * ((g.Lw + BW - 1) / BW) * (ep.CoutPad / 128);
     if (tiles4 >= NND_NUM_SMS) return launch_tc<128, 4, 1, 1, 6>(in, w, g, ep, st);
     return launch_tc<128, 2, 1, 2, 12>(in, w, g, ep, st);
   }
-  if (ep.Cout % 64 == 0) return g3 ? launch_tc<64, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<64, 4, 1, 2, 12>(in, w, g, ep, st);
+  if (ep.CoutPad % 64 == 0) return g3 ? launch_tc<64, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<64, 4, 1, 2, 12>(in, w, g, ep, st);
   return g3 ? launch_tc<32, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<32, 4, 1, 2, 12>(in, w, g, ep, st);
 }

@@ -233,3 +233,38 @@ def test_whole_network_backward_with_injected_output_gradients():
     bad = {k: (v, amp_err[k]) for k, v in worst.items() if v > 1.5 * amp_err[k] + 0.02}
     assert not bad, bad
     assert float(np.median(list(worst.values()))) <= 1.5 * float(np.median(list(amp_err.values()))) + 0.02
+
+
+def test_tcgen05_paths_match_mma_sync_paths_and_are_used():
+    """A/B: the tcgen05 kernels (fprop/dgrad incl. fp32 strided head outputs and stride-2 dgrad classes, wgrad) against
+    the mma.sync kernels on identical bf16 operands -- differences are fp32 accumulation order only."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200 import _lib as L
+    from ctypes import c_int
+    net, orc, arch, patch, bs = _build("tiny", 11)
+    images, _ = mo.synth_batch(patch, bs, arch["in_channels"], arch["classifier_classes"], 5)
+    g = torch.Generator().manual_seed(9)
+    outs = {}
+    for mode in ("mma", "tc"):
+        ops.set_tensor_path(mode == "tc")
+        L.lib().nnd_conv_set_wgrad_tc(c_int(1 if mode == "tc" else 0))
+        net.zero_grad(set_to_none=True)
+        pm, _, sm = net(images.cuda())
+        if mode == "mma":
+            gl = torch.randn(pm["box_logits"].shape, generator=g).cuda()
+            gd = torch.randn(pm["box_deltas"].shape, generator=g).cuda()
+            gs = (torch.randn(sm["seg_logits"].shape, generator=g) * 0.1).cuda()
+        torch.autograd.backward([pm["box_logits"], pm["box_deltas"], sm["seg_logits"]], [gl, gd, gs])
+        outs[mode] = (pm["box_logits"].detach().clone(), pm["box_deltas"].detach().clone(),
+                      {k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    ops.set_tensor_path(True)
+    L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+    assert rel_err(outs["tc"][0], outs["mma"][0]) < 2e-2 and rel_err(outs["tc"][1], outs["mma"][1]) < 2e-2
+    worst = max(rel_err(outs["tc"][2][k], outs["mma"][2][k]) for k in outs["mma"][2])
+    assert worst < 5e-2, worst
+    # the eligible layers really take the tcgen05 kernel
+    layer = net.encoder.stages[1].convs[0][1]               # 64 -> 64, 3x3x3, stride 1
+    x = torch.randn(2, 64, 8, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    plan = layer.plan(2, (8, 16, 16))
+    y = ops.empty_cl(2, 64, plan.out_sp)
+    assert ops.conv_gather(x, layer.packed()[0], plan.fprop[0], y, 64, 64) == 1
