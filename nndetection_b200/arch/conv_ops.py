@@ -172,3 +172,8 @@ def channel_sum(src: Tensor, rows: int, C: int, stride: int, out: Tensor, scale:
 
 def set_tensor_path(enable_tcgen05: bool):
     L.lib().nnd_conv_set_tensor_path(c_int(1 if enable_tcgen05 else 0))
+
+
+def set_stream_path(mode: int = 1, issuers: int = 2):
+    """0: off, 1: streaming z-window tcgen05 kernel where profitable (default), 2: wherever the shape is supported."""
+    L.lib().nnd_conv_set_stream_path(c_int(mode), c_int(issuers))

@@ -7,11 +7,19 @@
 int nnd_conv_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tcs_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tcs_profitable(const ConvGeom& g, const ConvEpilogue& ep);
+void nnd_conv_tcs_set_issuers(int n);
 int nnd_conv_wgrad(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                    long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                       long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_wgrad_tc32_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tc32_profitable(const ConvGeom& g);
+int nnd_conv_wgrad_tc32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ConvGeom& g, float* dw, long long s_co, long long s_ci,
+                        long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_halo_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                         long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
@@ -37,14 +45,20 @@ int parse_geom(const int* a, ConvGeom& g) {
 }
 int g_force_igemm = 0;
 int g_wgrad_tc = 1;
+int g_stream = 1;
 }  // namespace
 
 extern "C" {
 
 // 1: route eligible layers to the tcgen05 kernel (default), 0: always use the mma.sync kernel (cross-check / debugging)
 void nnd_conv_set_tensor_path(int enable_tcgen05) { g_force_igemm = !enable_tcgen05; }
-// 1 (default): tcgen05 wgrad where eligible; 0: mma.sync halo wgrad (A/B)
+// 1 (default): tcgen05 wgrad where eligible; 0: mma.sync halo wgrad (A/B); 2: also the stacked-tap 32-channel kernel on
+// volumes too small to fill the grid (tests)
 void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
+// 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
+// is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
+// issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
+void nnd_conv_set_stream_path(int enable, int issuers) { g_stream = enable; nnd_conv_tcs_set_issuers(issuers); }
 
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
@@ -55,6 +69,10 @@ int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* o
   ep.out = out; ep.out_n_stride = out_n_stride; ep.out_v_stride = out_v_stride; ep.out_fp32 = out_fp32;
   ep.Cout = Cout; ep.CoutPad = CoutPad; ep.bias = bias; ep.scale = scale;
   ep.residual = (const __nv_bfloat16*)residual; ep.stat_sum = stat_sum; ep.stat_sq = stat_sq;
+  if (!g_force_igemm && g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) {
+    if (used_tc) *used_tc = 2;
+    return nnd_conv_tcs((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+  }
   const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
   if (used_tc) *used_tc = tc ? 1 : 0;
   if (tc) return nnd_conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
@@ -65,6 +83,8 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g)))
+    return nnd_conv_wgrad_tc32((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_tc((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx))

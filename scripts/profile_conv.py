@@ -11,6 +11,9 @@ if len(sys.argv) > 6:
     from nndetection_b200 import _lib as L
     from ctypes import c_int
     L.lib().nnd_conv_set_wgrad_tc(c_int(int(sys.argv[6])))
+if os.environ.get("NND_STREAM"):                      # "mode,issuers" e.g. NND_STREAM=0,2 disables the streaming kernel
+    m_, i_ = (int(v) for v in os.environ["NND_STREAM"].split(","))
+    ops.set_stream_path(m_, i_)
 dev = torch.device("cuda")
 layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
 x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
@@ -33,4 +36,4 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 fl = 2.0 * 27 * cin * cout * bs * size ** 3
-print(f"{mode} {cin}->{cout} @{size}^3 x{bs}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+print(f"{mode} {cin}->{cout} @{size}^3 x{bs} stream={os.environ.get('NND_STREAM', 'default')}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  (kernel code {run()})")

@@ -260,11 +260,129 @@ def test_tcgen05_paths_match_mma_sync_paths_and_are_used():
     ops.set_tensor_path(True)
     L.lib().nnd_conv_set_wgrad_tc(c_int(1))
     assert rel_err(outs["tc"][0], outs["mma"][0]) < 2e-2 and rel_err(outs["tc"][1], outs["mma"][1]) < 2e-2
+    # Whole-network gradients of two bf16 implementations differ by re-rounding noise that the instance norms amplify
+    # (each is ~0.1-0.2 away from the fp32 oracle, as is stock autocast: gpurun_out/grad_err.json); the tight A/B gate
+    # is the per-layer test below, this one only catches gross errors.
     worst = max(rel_err(outs["tc"][2][k], outs["mma"][2][k]) for k in outs["mma"][2])
-    assert worst < 5e-2, worst
+    assert worst < 0.35, worst
     # the eligible layers really take the tcgen05 kernel
     layer = net.encoder.stages[1].convs[0][1]               # 64 -> 64, 3x3x3, stride 1
     x = torch.randn(2, 64, 8, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
     plan = layer.plan(2, (8, 16, 16))
     y = ops.empty_cl(2, 64, plan.out_sp)
     assert ops.conv_gather(x, layer.packed()[0], plan.fprop[0], y, 64, 64) == 1
+
+
+AB_CASES = [
+    (32, 32, 3, 1, (2, 8, 16, 16)),            # 32-channel full-resolution layer class
+    (64, 64, 3, 1, (2, 8, 16, 16)),
+    (128, 128, 3, 1, (1, 8, 16, 8)),
+    (128, 128, (1, 3, 3), 1, (1, 4, 16, 16)),
+    (32, 64, 3, 2, (2, 12, 16, 20)),           # stride-2: dgrad runs as parity classes
+    (64, 128, 3, (1, 2, 2), (1, 6, 16, 16)),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,s,shape", AB_CASES)
+def test_tcgen05_vs_mma_sync_single_layer(cin, cout, k, s, shape):
+    """Same bf16 operands through the tcgen05 kernels and through the mma.sync kernels: only the fp32 accumulation
+    order differs -> 2e-3 in norm on the bf16 outputs (one output ulp = 2^-8), 1e-3 on the fp32 weight gradient."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200 import _lib as L
+    from ctypes import c_int
+    mine, _ = make_pair("instance", cin, cout, k, s, norm=False)
+    g = torch.Generator().manual_seed(21)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g)).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    res = {}
+    try:
+        for mode in ("mma", "tc"):
+            ops.set_tensor_path(mode == "tc")
+            L.lib().nnd_conv_set_wgrad_tc(c_int(1 if mode == "tc" else 0))
+            mine.zero_grad(set_to_none=True)
+            xm = x.clone().requires_grad_(True)
+            y = mine(xm)
+            if mode == "mma":
+                gy = q(torch.randn(y.shape, generator=g)).cuda().to(torch.bfloat16)
+            y.backward(gy)
+            res[mode] = (y.detach().float(), xm.grad.float(), mine.conv.weight.grad.clone())
+    finally:
+        ops.set_tensor_path(True)
+        L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+    assert rel_err(res["tc"][0], res["mma"][0]) < 2e-3
+    assert rel_err(res["tc"][1], res["mma"][1]) < 2e-3
+    assert rel_err(res["tc"][2], res["mma"][2]) < 1e-3
+
+
+TCS_CASES = [
+    # cin, cout, shape [N, D, H, W], issuers  -- D > 16 wraps the TMEM ring, odd H / W exercise partial tiles
+    (32, 32, (2, 20, 24, 40), 2),
+    (32, 32, (1, 37, 21, 19), 1),
+    (64, 64, (1, 18, 32, 24), 2),
+    (32, 64, (1, 9, 16, 16), 2),               # two output tiles (weights reloaded); its dgrad is the 64 -> 32 form
+    (64, 32, (2, 5, 17, 9), 1),
+]
+
+
+@pytest.mark.parametrize("cin,cout,shape,issuers", TCS_CASES)
+def test_streaming_zwindow_conv_block_vs_oracle(cin, cout, shape, issuers):
+    """conv_tcs.cu (N = 96 z-window MMAs, TMEM ring) forced on: fprop + norm statistics + dgrad against the CPU oracle,
+    and against the tile kernel on identical operands (accumulation order only)."""
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair("instance", cin, cout, 3, 1)
+    g = torch.Generator().manual_seed(31)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res = {}
+    try:
+        for mode in (2, 0):
+            ops.set_stream_path(mode, issuers)
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            ym = mine(xm)
+            ym.backward(gy.cuda().to(torch.bfloat16))
+            res[mode] = (ym.detach().float().cpu(), xm.grad.float().cpu(), mine.norm.weight.grad.cpu().clone())
+        # the layer really takes the streaming kernel when forced
+        ops.set_stream_path(2, issuers)
+        plan = mine.plan(shape[0], tuple(shape[1:]))
+        xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+        y = ops.empty_cl(shape[0], cout, plan.out_sp)
+        assert ops.conv_gather(xm, mine.packed()[0], plan.fprop[0], y, cout, cout) == 2
+    finally:
+        ops.set_stream_path(1, 2)
+    ym, gx, gg = res[2]
+    assert rel_err(ym, yr.detach()) < 1e-2
+    torch.testing.assert_close(ym, yr.detach(), rtol=3e-2, atol=3e-2)
+    assert rel_err(gx, xr.grad) < 3e-2
+    assert rel_err(gg, ref.norm.weight.grad) < 4e-2
+    assert rel_err(ym, res[0][0]) < 2e-3 and rel_err(gx, res[0][1]) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 17, 21), (1, 4, 32, 48), (1, 2, 8, 16)])
+def test_stacked_tap_wgrad_32_channels(shape):
+    """conv_wgrad_tc32.cu (dz taps stacked along M, dy taps along N, dx taps as start offsets) forced on: fp32 dW against
+    the CPU oracle on bf16-exact operands (5e-3) and against the mma.sync wgrad (accumulation order only, 1e-3)."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200 import _lib as L
+    from ctypes import c_int
+    mine, ref = make_pair("instance", 32, 32, 3, 1, norm=False)
+    g = torch.Generator().manual_seed(41)
+    x = q(torch.randn(shape[0], 32, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res = {}
+    try:
+        for mode in (2, 0):
+            L.lib().nnd_conv_set_wgrad_tc(c_int(mode))
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            mine(xm).backward(gy.cuda().to(torch.bfloat16))
+            res[mode] = mine.conv.weight.grad.cpu().clone()
+    finally:
+        L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+    assert rel_err(res[2], ref.conv.weight.grad) < 5e-3
+    assert rel_err(res[2], res[0]) < 1e-3
