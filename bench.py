@@ -276,6 +276,10 @@ def main():
                        "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                "train_tflops": 3 * conv_flops_per_patch(arch, patch) * bs * world * args.steps / (ms / 1e3) / 1e12}
+        try:
+            out["nms"] = nms_rates(dev)
+        except Exception as e:
+            out["nms"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = cpu_baseline()
@@ -319,6 +323,36 @@ def conv_roofline(net, dev, arch, patch, bs):
             "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst, "peak_kind": kind + " burst bf16 cuBLAS",
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": None}
+
+
+def nms_rates(dev):
+    """BASELINE.json's second metric: 3-D NMS boxes/s = N / time of ONE nndet._C.nms call (sort included), SURVEY 8d stress
+    boxes (centres U[0,160)^3, half sizes U[2,22), unique scores), thr 0.1; bytes = 28N + 8N + 8 N ceil(N/64) (upper
+    triangle written once, read once) + 8K; pair tests = N (N-1) / 2."""
+    from nndetection_b200 import _C
+    res = {}
+    for n in (10_000, 100_000):
+        g = torch.Generator().manual_seed(7)
+        c = torch.rand(n, 3, generator=g) * 160
+        h = torch.rand(n, 3, generator=g) * 20 + 2
+        boxes = torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1], c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], 1).to(dev)
+        scores = ((torch.randperm(n, generator=g).float() + 0.5) / n).to(dev)
+        for _ in range(2):
+            keep = _C.nms(boxes, scores, 0.1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        it = 10 if n <= 10_000 else 3
+        e0.record()
+        for _ in range(it):
+            keep = _C.nms(boxes, scores, 0.1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / it
+        k = int(keep.numel())
+        byt = 36.0 * n + 8.0 * n * ((n + 63) // 64) + 8.0 * k
+        res[f"n{n}"] = {"ms": ms, "boxes_per_s": n / (ms / 1e3), "kept": k, "algorithmic_GB_per_s": byt / (ms / 1e3) / 1e9,
+                        "pair_tests_per_s": 0.5 * n * (n - 1) / (ms / 1e3)}
+    return res
 
 
 def cpu_baseline():

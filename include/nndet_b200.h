@@ -38,6 +38,15 @@ int nnd_nms3d_f32(const float* boxes, const float* scores, long long n, float io
 int nnd_nms2d_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long* keep_out,
                   long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+/* ---- weighted box clustering.  Replaces wbc + compute_cluster_consolidation, nndet/inference/detection/wbc.py:94-198
+ *      (N x N IoU matrix + python while loop with torch.where per cluster).  boxes [n, 6], scores / weights / n_exp_preds [n];
+ *      clusters in descending head-score order; out_boxes [n, 6], out_scores [n], n_out device scalar (clusters with
+ *      score > score_thresh). */
+size_t nnd_wbc_workspace_bytes(long long n);
+int nnd_wbc3d_f32(const float* boxes, const float* scores, const float* weights, const float* n_exp_preds, long long n,
+                  float iou_thresh, float score_thresh, int use_area, float missing_weight, float* out_boxes,
+                  float* out_scores, long long* n_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 /* ---- anchors: one pyramid level of AnchorGenerator3D.grid_anchors, nndet/core/boxes/anchors.py:337-377.
  *      out [s0*s1*s2*nb, 6]; base [nb, 6] (generate_anchors, anchors.py:526-549); size3/stride3 host ints. */
 int nnd_anchor_grid_f32(float* out, const float* base, int nb, const int* size3_host, const int* stride3_host, cudaStream_t stream);
@@ -112,6 +121,7 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
 int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom_host, int Cout, void* out, float* stat_sum,
                              float* stat_sq, cudaStream_t stream);
 int nnd_conv_first_wgrad_f32(const float* x, const void* dy, const int* geom_host, int Cout, float* dw, cudaStream_t stream);
+void nnd_conv_set_first_layer_mma(int enable);       /* A/B switch: tensor-core image layer (default) vs scalar kernels */
 /* fp32 master weight ([Cout][Cin][T], or [Cin][Cout][T] if transposed) -> bf16 fprop / dgrad operands */
 int nnd_pack_weights(const float* w, int Cout, int Cin, int T, int transposed, void* fwd, int CoutPadF, int CinPadF, void* bwd,
                      int CinPadB, int CoutPadB, cudaStream_t stream);

@@ -144,10 +144,18 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
 
 }  // namespace
 
+int nnd_conv_first_mma_supported(const ConvGeom& g, int Cout);
+int nnd_conv_first_fprop_mma(const float* x, const float* w, const ConvGeom& g, __nv_bfloat16* out, float* stat_sum,
+                             float* stat_sq, cudaStream_t st);
+int nnd_conv_first_wgrad_mma(const float* x, const __nv_bfloat16* dy, const ConvGeom& g, float* dw, cudaStream_t st);
+static int g_first_mma = 1;
+extern "C" void nnd_conv_set_first_layer_mma(int enable) { g_first_mma = enable; }   // A/B: 0 = scalar CUDA-core kernels
+
 // x fp32 [N, Cin, D, H, W] (NCDHW), w fp32 [Cout][Cin][T]; geometry: stride 1, Ld/Lh/Lw == Di/Hi/Wi.
 int nnd_conv_first_fprop(const float* x, const float* w, const ConvGeom& g, int Cout, __nv_bfloat16* out,
                          float* stat_sum, float* stat_sq, cudaStream_t st) {
   if (!x || !w || !out || g.Cin < 1 || g.Cin > FIRST_MAX_CIN) return NND_ERR_ARG;
+  if (g_first_mma && nnd_conv_first_mma_supported(g, Cout)) return nnd_conv_first_fprop_mma(x, w, g, out, stat_sum, stat_sq, st);
   const int V = g.Ld * g.Lh * g.Lw;
   dim3 grid((V + 127) / 128, g.N);
   const size_t smem = (size_t)g.T * g.Cin * Cout * sizeof(float);
@@ -164,6 +172,7 @@ int nnd_conv_first_wgrad(const float* x, const __nv_bfloat16* dy, const ConvGeom
   if (!x || !dy || !dw || g.Cin < 1 || g.Cin > FIRST_MAX_CIN || g.T > 27) return NND_ERR_ARG;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return NND_ERR_ARG;
+  if (g_first_mma && nnd_conv_first_mma_supported(g, Cout)) return nnd_conv_first_wgrad_mma(x, dy, g, dw, st);
   const int rows_per_d = (g.Lh + FW_ROWS - 1) / FW_ROWS;
   const unsigned blocks = (unsigned)(g.N * g.Ld * rows_per_d);
   const size_t smem = (size_t)9 * (g.Lw + 2) * sizeof(float) + (size_t)g.Lw * 32 * sizeof(__nv_bfloat16);

@@ -140,7 +140,7 @@ __device__ __forceinline__ Item decode_item(int idx, const TcsTiles& tl, int D) 
 }
 
 // A_SLOTS input slices in the ring, of which LAG + 1 may still be in flight (published LAG slices late)
-template <int CIN, int NI, int A_SLOTS, int LAG>
+template <int CIN, int NI, int A_SLOTS, int LAG, bool STATS>
 __global__ void __launch_bounds__((4 + NI + 4) * 32, 1)
 conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
                 const ConvEpilogue ep, const TcsTiles tl) {
@@ -160,6 +160,7 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
   __shared__ unsigned s_tmem_base;
   __shared__ int s_wtap[27];                       // weight slice of the tap with offsets (dz, dy, dx), index (dz+1)*9+(dy+1)*3+(dx+1)
   __shared__ float s_stat[2][4][NB];
+  __shared__ __align__(16) float s_bias[NB];
   const unsigned bar0 = smem_u32(bars);
   auto HFULL = [&](int i) { return bar0 + 8u * i; };
   auto HEMPTY = [&](int i) { return bar0 + 8u * (A_SLOTS + i); };
@@ -307,11 +308,14 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
     }
   } else {
     // ================================================================ epilogue (warp q owns TMEM lanes 32q .. 32q+31)
+    // Per output slice a warp only does: TMEM load, zero + release the slot, (bias / residual / scale), bf16 pack, 64-byte
+    // row store, and 64 FMAs into per-thread statistics; the cross-lane reduction of the statistics happens once per
+    // work item (the epilogue warps are the critical path of this kernel: ~150 instead of ~700 instructions per slice).
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int hy = row >> 3, wx = row & 7;
     const float scale = ep.scale ? *ep.scale : 1.f;
-    const bool do_stats = ep.stat_sum != nullptr;
+    const bool has_scale = ep.scale != nullptr;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.out);
     int g_base = 0;
     for (int idx = blockIdx.x; idx < tl.total; idx += gridDim.x) {
@@ -319,11 +323,21 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
       const int h = it.h0 + hy, w = it.w0 + wx;
       const bool hw_ok = h < g.Lh && w < g.Lw;
       const int co0 = it.nt * NB;
-      float bias_l = 0.f;
-      if (ep.bias) bias_l = ep.bias[co0 + lane];
-      if (do_stats) { s_stat[0][q][lane] = 0.f; s_stat[1][q][lane] = 0.f; }
+      if (ep.bias) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = tid - (4 + NI) * 32;
+        if (et < NB) s_bias[et] = ep.bias[co0 + et];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      float ssum[STATS ? 32 : 1], ssq[STATS ? 32 : 1];
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
+      }
+      long long vox = ((long long)(it.n * g.Do + it.z0) * g.Ho + h) * g.Wo + w;
+      const long long vox_step = (long long)g.Ho * g.Wo;
 #pragma unroll 1
-      for (int m = it.z0; m < it.z1; ++m) {
+      for (int m = it.z0; m < it.z1; ++m, vox += vox_step) {
         const int gi = g_base + (m - it.z0);
         const int slot = gi % ACC_SLOTS;
         mbar_wait_warp(AFULL(slot), (unsigned)(gi / ACC_SLOTS) & 1u, lane);
@@ -335,53 +349,54 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(AEMPTY(slot));
-        const long long vox = ((long long)(it.n * g.Do + m) * g.Ho + h) * g.Wo + w;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         if (ep.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bias_l, j);
-        }
-        if (ep.residual && hw_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + vox * ep.Cout + co0);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 rv = rp[u];
-            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 t2 = __bfloat1622float2(hp[k]);
-              f[u * 8 + 2 * k] += t2.x; f[u * 8 + 2 * k + 1] += t2.y;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[j]);
+            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
           }
         }
-        __align__(16) __nv_bfloat162 pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          pk[j] = __floats2bfloat162_rn(f[2 * j] * scale, f[2 * j + 1] * scale);
-          const float2 r2 = __bfloat1622float2(pk[j]);
-          f[2 * j] = hw_ok ? r2.x : 0.f; f[2 * j + 1] = hw_ok ? r2.y : 0.f;
-        }
         if (hw_ok) {
+          if (ep.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + vox * ep.Cout + co0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = rp[u];
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 t2 = __bfloat1622float2(hp[k]);
+                f[u * 8 + 2 * k] += t2.x; f[u * 8 + 2 * k + 1] += t2.y;
+              }
+            }
+          }
+          if (has_scale) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= scale;
+          }
+          __align__(16) __nv_bfloat162 pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
           uint4* op = reinterpret_cast<uint4*>(outp + vox * ep.Cout + co0);
           const uint4* sp = reinterpret_cast<const uint4*>(pk);
 #pragma unroll
           for (int u = 0; u < 4; ++u) op[u] = sp[u];
-        }
-        if (do_stats) {
-          float sq[32];
+          if (STATS) {                              // statistics of the fp32 values (the stored bf16 differs by < 2^-9 relative)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-          int col;
-          const float cs = warp_transpose_reduce32(f, lane, col);
-          const float cq = warp_transpose_reduce32(sq, lane, col);
-          s_stat[0][q][col] += cs;                  // col is a permutation of the lanes
-          s_stat[1][q][col] += cq;
+            for (int j = 0; j < 32; ++j) { ssum[j] += f[j]; ssq[j] = fmaf(f[j], f[j], ssq[j]); }
+          }
         }
       }
       g_base += it.z1 - it.z0;
-      if (do_stats) {
+      if (STATS) {
+        int col;
+        const float cs = warp_transpose_reduce32(ssum, lane, col);
+        const float cq = warp_transpose_reduce32(ssq, lane, col);
+        s_stat[0][q][col] = cs;                    // col is a permutation of the lanes
+        s_stat[1][q][col] = cq;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const int et = tid - (4 + NI) * 32;          // 0..127
         if (et < NB) {
@@ -405,7 +420,7 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
 
 int g_tcs_issuers = 2;
 
-template <int CIN, int NI, int A_SLOTS, int LAG>
+template <int CIN, int NI, int A_SLOTS, int LAG, bool STATS>
 int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   TcsTiles tl;
   tl.HB = (g.Lh + BH - 1) / BH; tl.WB = (g.Lw + BW - 1) / BW; tl.NT = ep.Cout / NB;
@@ -426,11 +441,11 @@ int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
   constexpr size_t SMEM = (size_t)9 * (CIN / 8) * WROW + (size_t)A_SLOTS * (CIN / 8) * GP + 8 * (2 * A_SLOTS + 2 * ACC_SLOTS);
   static bool attr_set = false;
   if (!attr_set) {
-    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tcs_kernel<CIN, NI, A_SLOTS, LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tcs_kernel<CIN, NI, A_SLOTS, LAG, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
-  conv_tcs_kernel<CIN, NI, A_SLOTS, LAG><<<grid, (4 + NI + 4) * 32, SMEM, st>>>(in, w, g, ep, tl);
+  conv_tcs_kernel<CIN, NI, A_SLOTS, LAG, STATS><<<grid, (4 + NI + 4) * 32, SMEM, st>>>(in, w, g, ep, tl);
   NND_LAUNCH_CHECK("conv_tcs_kernel");
   return NND_OK;
 }
@@ -464,6 +479,11 @@ int nnd_conv_tcs_profitable(const ConvGeom& g, const ConvEpilogue& ep) {
 
 int nnd_conv_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   if (!nnd_conv_tcs_supported(g, ep)) return NND_ERR_ARG;
-  if (g.Cin == 32) return g_tcs_issuers == 1 ? launch_tcs<32, 1, 12, 5>(in, w, g, ep, st) : launch_tcs<32, 2, 12, 5>(in, w, g, ep, st);
-  return g_tcs_issuers == 1 ? launch_tcs<64, 1, 4, 2>(in, w, g, ep, st) : launch_tcs<64, 2, 4, 2>(in, w, g, ep, st);
+  const bool st2 = ep.stat_sum != nullptr;
+  if (g.Cin == 32) {
+    if (g_tcs_issuers == 1) return st2 ? launch_tcs<32, 1, 12, 5, true>(in, w, g, ep, st) : launch_tcs<32, 1, 12, 5, false>(in, w, g, ep, st);
+    return st2 ? launch_tcs<32, 2, 12, 5, true>(in, w, g, ep, st) : launch_tcs<32, 2, 12, 5, false>(in, w, g, ep, st);
+  }
+  if (g_tcs_issuers == 1) return st2 ? launch_tcs<64, 1, 4, 2, true>(in, w, g, ep, st) : launch_tcs<64, 1, 4, 2, false>(in, w, g, ep, st);
+  return st2 ? launch_tcs<64, 2, 4, 2, true>(in, w, g, ep, st) : launch_tcs<64, 2, 4, 2, false>(in, w, g, ep, st);
 }

@@ -215,7 +215,15 @@ conv_wgrad_tc_kernel(const WtArgs a) {
     // ================================================================ epilogue: TMEM -> fp32 atomics into dW
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    mbar_wait(DONE, 0);
+    if (lane == 0) {                               // one poller per warp, with backoff: the wait lasts the whole kernel
+      unsigned ok = 0;
+      while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(DONE), "r"(0u) : "memory");
+        if (!ok) __nanosleep(1000);
+      }
+    }
+    __syncwarp();
     tc_fence_after();
 #pragma unroll 1
     for (int tap = 0; tap < 3; ++tap) {

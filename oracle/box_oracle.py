@@ -310,6 +310,61 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, t
     return nms_greedy(boxes + off[:, None], scores, thr, cuda_semantics)
 
 
+# --------------------------------------------------------------------------- weighted box clustering
+def wbc(boxes: torch.Tensor, scores: torch.Tensor, weights: torch.Tensor, n_exp_preds: torch.Tensor, iou_thresh: float,
+        score_thresh: float, use_area: bool = True, missing_weight: float = 1.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """wbc + compute_cluster_consolidation, nndet/inference/detection/wbc.py:94-198, restated without the N x N matrix:
+    boxes in descending score order (stable: ties by ascending index); the highest remaining box heads a cluster of all
+    remaining boxes with IoU > iou_thresh to it (:133-134, itself included since IoU(h, h) = 1; a zero-volume head has
+    NaN IoU with itself and disappears with an empty cluster); score = sum(iou*w*s) / (sum(iou*w) + max(0, mean(n_exp) -
+    n_found) * mean(iou*w) * missing_weight) (:185-191); box = sum(box * iou*w*s) / sum(iou*w*s) (:193-194); clusters whose
+    score is not > score_thresh are dropped (:149)."""
+    n = boxes.shape[0]
+    if n == 0:
+        return boxes.new_zeros((0, boxes.shape[1])), scores.new_zeros((0,))
+    b = boxes.float()
+    w = weights.float() * box_volume(b) if use_area else weights.float()
+    order = torch.argsort(-scores.float(), stable=True)
+    alive = torch.ones(n, dtype=torch.bool)
+    out_b, out_s = [], []
+    for oi in range(n):
+        h = int(order[oi])
+        if not alive[h]:
+            continue
+        pool = order[oi:][alive[order[oi:]]]
+        iou = iou_union_3d(b[h:h + 1], b[pool])[0][0]
+        m = iou > iou_thresh
+        idx = pool[m]
+        alive[h] = False                       # NaN IoU with itself: neither matched nor kept in the pool (:152-153)
+        alive[idx] = False
+        if idx.numel() == 0:
+            continue
+        iou_m = iou[m]
+        msw = iou_m * w[idx]
+        ms = msw * scores[idx].float()
+        n_missing = torch.clamp(n_exp_preds[idx].float().mean() - idx.numel(), min=0.0)
+        denom = msw.sum() + n_missing * msw.mean() * missing_weight
+        sc = ms.sum() / denom
+        if bool(sc > score_thresh):
+            out_b.append((b[idx] * ms[:, None]).sum(0) / ms.sum())
+            out_s.append(sc)
+    if not out_b:
+        return boxes.new_zeros((0, boxes.shape[1])), scores.new_zeros((0,))
+    return torch.stack(out_b), torch.stack(out_s)
+
+
+def batched_wbc(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh, use_area=False, missing_weight=1.0):
+    """batched_wbc, wbc.py:30-91: per label (ascending), results concatenated; labels returned in the scores' dtype."""
+    ob, os_, ol = [], [], []
+    for lab in labels.unique():
+        m = labels == lab
+        b, s = wbc(boxes[m], scores[m], weights[m], n_exp_preds[m], iou_thresh, score_thresh, use_area, missing_weight)
+        ob.append(b); os_.append(s); ol.append(torch.empty_like(s).fill_(float(lab)))
+    if not ob:
+        return boxes.new_zeros((0, boxes.shape[1])), scores.new_zeros((0,)), scores.new_zeros((0,))
+    return torch.cat(ob), torch.cat(os_), torch.cat(ol)
+
+
 # --------------------------------------------------------------------------- detection post-processing
 def postprocess_single_image(boxes: torch.Tensor, probs: torch.Tensor, image_shape: Sequence[int],
                              num_classes: int, topk: int = 10000, score_thresh: Optional[float] = 0.0,

@@ -61,6 +61,40 @@ def unique_scores(n, g):
     return (torch.randperm(n, generator=g).float() + 0.5) / max(n, 1)
 
 
+# ------------------------------------------------------------------------------------------ weighted box clustering
+def wbc_case(n, seed, extent=60.0):
+    g = torch.Generator().manual_seed(seed)
+    boxes = rand_boxes(n, g, extent=extent, lo=2.0, hi=10.0)
+    scores = unique_scores(n, g)
+    weights = torch.rand(n, generator=g) * 0.9 + 0.1
+    n_exp = torch.randint(1, 9, (n,), generator=g).float()
+    return boxes, scores, weights, n_exp
+
+
+def gen_wbc():
+    """nndet/inference/detection/wbc.py loaded from its file (the package __init__ pulls SimpleITK-dependent io modules)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_wbc", os.path.join(ref_import.REF_ROOT, "nndet/inference/detection/wbc.py"))
+    rw = importlib.util.module_from_spec(spec); spec.loader.exec_module(rw)
+    out, cases = {}, []
+    for n, seed, thr, st, ua, mw in [(1, 1, 0.1, 0.0, True, 1.0), (50, 2, 0.1, 0.0, True, 0.7), (300, 3, 0.3, 0.05, False, 1.0),
+                                     (1000, 4, 1e-5, 0.1, True, 0.5), (1000, 5, 0.5, 0.0, True, 1.0), (2500, 6, 0.2, 0.02, True, 1.0)]:
+        b, s, w, ne = wbc_case(n, seed, extent=60.0 if n <= 1000 else 100.0)
+        rb, rs = rw.wbc(b, s, w, ne, thr, st, use_area=ua, missing_weight=mw)
+        ob, os_ = bo.wbc(b, s, w, ne, thr, st, use_area=ua, missing_weight=mw)
+        rs = rs.flatten()
+        assert rb.shape == ob.shape and torch.equal(rb, ob) and torch.equal(rs, os_), (n, thr)
+        cases.append((n, seed, thr, st, int(ua), mw))
+        out[f"c{len(cases) - 1}_boxes"] = rb; out[f"c{len(cases) - 1}_scores"] = rs
+    b, s, w, ne = wbc_case(600, 9)
+    lab = torch.randint(0, 3, (600,), generator=torch.Generator().manual_seed(5))
+    r = rw.batched_wbc(b, s, lab, w, 0.2, ne, 0.02, use_area=True, missing_weight=1.0)
+    o = bo.batched_wbc(b, s, lab, w, 0.2, ne, 0.02, use_area=True, missing_weight=1.0)
+    assert torch.equal(r[0], o[0]) and torch.equal(r[1].flatten(), o[1]) and torch.equal(r[2].flatten(), o[2])
+    save("wbc", cases=np.asarray(cases, dtype=np.float64), batched_labels_in=lab, batched_boxes=r[0], batched_scores=r[1].flatten(),
+         batched_labels=r[2].flatten(), **out)
+
+
 # ------------------------------------------------------------------------------------------ box metrics
 def gen_pairwise():
     g = torch.Generator().manual_seed(11)
@@ -328,7 +362,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -357,7 +357,9 @@ def test_streaming_zwindow_conv_block_vs_oracle(cin, cout, shape, issuers):
     torch.testing.assert_close(ym, yr.detach(), rtol=3e-2, atol=3e-2)
     assert rel_err(gx, xr.grad) < 3e-2
     assert rel_err(gg, ref.norm.weight.grad) < 4e-2
-    assert rel_err(ym, res[0][0]) < 2e-3 and rel_err(gx, res[0][1]) < 2e-3
+    # vs the tile kernel: identical operands; the norm statistics differ in the last bits (fp32 vs bf16-rounded values),
+    # which flips a few ReLU masks in the backward -> looser bound on dx
+    assert rel_err(ym, res[0][0]) < 2e-3 and rel_err(gx, res[0][1]) < 2e-2
 
 
 @pytest.mark.parametrize("shape", [(2, 9, 17, 21), (1, 4, 32, 48), (1, 2, 8, 16)])
@@ -386,3 +388,33 @@ def test_stacked_tap_wgrad_32_channels(shape):
         L.lib().nnd_conv_set_wgrad_tc(c_int(1))
     assert rel_err(res[2], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[2], res[0]) < 1e-3
+
+
+@pytest.mark.parametrize("cin,shape", [(1, (2, 10, 12, 14)), (1, (1, 9, 20, 70)), (2, (1, 6, 17, 33))])
+def test_image_layer_tensor_core_vs_scalar_kernels(cin, shape):
+    """conv_first_mma.cu (bf16 operands, mma.sync, fp32 accumulate) against the scalar fp32 kernels of conv_first.cu on
+    the same tensors: forward + norm statistics through the block, dW by calling both wgrad kernels on ONE (x, dy) pair
+    (through the block a re-rounded pre-activation flips ReLU masks and changes dy itself).  Differences = bf16 rounding
+    of image and weights (2^-9 relative per operand): 5e-3 forward, 1e-2 dW (dW of an instance-normalised layer is a
+    difference of large sums: sum(dy) = 0)."""
+    from nndetection_b200 import _lib as L
+    from nndetection_b200.arch import conv_ops as ops
+    from ctypes import c_int
+    mine, _ = make_pair("instance", cin, 32, 3, 1)
+    g = torch.Generator().manual_seed(51)
+    x = torch.rand(shape[0], cin, *shape[1:], generator=g).cuda()
+    dy = q(torch.randn(shape[0], *shape[1:], 32, generator=g)).cuda().to(torch.bfloat16).permute(0, 4, 1, 2, 3)
+    plan = mine.plan(shape[0], tuple(shape[1:]))
+    res = {}
+    try:
+        for mode in (0, 1):
+            L.lib().nnd_conv_set_first_layer_mma(c_int(mode))
+            with torch.no_grad():
+                y = mine(x)
+            dw = torch.zeros_like(mine.conv.weight)
+            ops.conv_first_wgrad(x, dy, plan.fprop[0], 32, dw)
+            res[mode] = (y.float(), dw)
+    finally:
+        L.lib().nnd_conv_set_first_layer_mma(c_int(1))
+    assert rel_err(res[1][0], res[0][0]) < 5e-3
+    assert rel_err(res[1][1], res[0][1]) < 1e-2

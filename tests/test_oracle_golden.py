@@ -104,3 +104,18 @@ def test_model_oracle_matches_reference_golden():
     for i in range(bs):
         assert torch.equal(post[i][2], T(g[f"det_labels{i}"]))
         assert torch.allclose(post[i][0], T(g[f"det_boxes{i}"]), atol=1e-4)
+
+
+def test_wbc_oracle_matches_reference_fixtures():
+    """oracle.box_oracle.wbc / batched_wbc vs the executed reference (nndet/inference/detection/wbc.py), bit-exact."""
+    g = util.golden("wbc")
+    for i, (n, seed, thr, st, ua, mw) in enumerate(g["cases"].tolist()):
+        n, seed = int(n), int(seed)
+        b, s, w, ne = util.wbc_case(n, seed, extent=60.0 if n <= 1000 else 100.0)
+        ob, os_ = bo.wbc(b, s, w, ne, thr, st, use_area=bool(ua), missing_weight=mw)
+        assert torch.equal(ob, torch.from_numpy(g[f"c{i}_boxes"])) and torch.equal(os_, torch.from_numpy(g[f"c{i}_scores"]))
+    b, s, w, ne = util.wbc_case(600, 9)
+    lab = torch.from_numpy(g["batched_labels_in"])
+    o = bo.batched_wbc(b, s, lab, w, 0.2, ne, 0.02, use_area=True, missing_weight=1.0)
+    assert torch.equal(o[0], torch.from_numpy(g["batched_boxes"])) and torch.equal(o[1], torch.from_numpy(g["batched_scores"]))
+    assert torch.equal(o[2], torch.from_numpy(g["batched_labels"]))

@@ -44,3 +44,13 @@ def det_fill(sd, seed=0):
             fan_in = int(np.prod(v.shape[1:])) if v.ndim > 1 else 1
             out[k] = torch.from_numpy(rs.standard_normal(v.shape) * (1.5 / np.sqrt(fan_in))).to(v.dtype)
     return out
+
+
+def wbc_case(n, seed, extent=60.0):
+    """Same generator as scripts/gen_golden.py:wbc_case."""
+    g = torch.Generator().manual_seed(seed)
+    boxes = rand_boxes(n, g, extent=extent, lo=2.0, hi=10.0)
+    scores = unique_scores(n, g)
+    weights = torch.rand(n, generator=g) * 0.9 + 0.1
+    n_exp = torch.randint(1, 9, (n,), generator=g).float()
+    return boxes, scores, weights, n_exp
