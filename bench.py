@@ -318,11 +318,16 @@ def conv_roofline(net, dev, arch, patch, bs):
     vox = bs * patch[0] * patch[1] * patch[2]
     flops = 2.0 * 27 * cin * cout * vox
     achieved = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_tc (tcgen05)" if used else "conv_igemm_kernel<32> (mma.sync)",
+    kname = {2: "conv_tcs_kernel (tcgen05, streaming z-window N=96 MMAs)", 1: "conv_tc_kernel (tcgen05 tile kernel)"}.get(used, "conv_igemm_kernel<32> (mma.sync)")
+    # DRAM traffic of this launch from the committed `ncu --set full` capture (profiles/r01_ncu_conv_tcs32_summary.txt):
+    # dram__bytes_read.sum 545.0 MB + dram__bytes_write.sum 483.8 MB -- equals the algorithmic bytes (no re-reads)
+    traffic = 544.989952e6 + 483.824384e6 if used == 2 else None
+    return {"bound": "tensor", "kernel": kname,
             "layer": f"encoder.stage0.conv2 {cin}->{cout} 3x3x3 @ {patch[0]}^3 x batch {bs}",
             "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst, "peak_kind": kind + " burst bf16 cuBLAS",
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
-            "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": None}
+            "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": traffic,
+            "traffic_source": "profiles/r01_ncu_conv_tcs32_summary.txt (ncu --set full, same layer and shape)"}
 
 
 def nms_rates(dev):

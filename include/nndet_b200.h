@@ -47,6 +47,16 @@ int nnd_wbc3d_f32(const float* boxes, const float* scores, const float* weights,
                   float iou_thresh, float score_thresh, int use_area, float missing_weight, float* out_boxes,
                   float* out_scores, long long* n_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+/* ---- instance segmentation -> detection targets.  Replaces the per-step `pre_trafo` chain FindInstances /
+ *      Instances2Boxes / Instances2Segmentation, nndet/io/transforms/instances.py:25-39,42-136,211-301 (invoked at
+ *      nndet/ptmodule/retinaunet/base.py:140-141).  target / sem_out fp32 [B, D, H, W]; lut_sem / lut_class int32 [B, max_id]
+ *      (label written to the semantic map resp. class of the instance, -1 = id not in the mapping); outputs padded to `cap`
+ *      instances per sample, ids ascending; err_out bit 0: id >= max_id or non-integer, bit 1: id missing in the mapping. */
+size_t nnd_instances_workspace_bytes(int B, int max_id);
+int nnd_instances_to_targets(const float* target, int B, int D, int H, int W, const int* lut_sem, const int* lut_class,
+                             int max_id, int cap, float* sem_out, int* out_ids, float* out_boxes, long long* out_classes,
+                             int* counts, int* err_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 /* ---- anchors: one pyramid level of AnchorGenerator3D.grid_anchors, nndet/core/boxes/anchors.py:337-377.
  *      out [s0*s1*s2*nb, 6]; base [nb, 6] (generate_anchors, anchors.py:526-549); size3/stride3 host ints. */
 int nnd_anchor_grid_f32(float* out, const float* base, int nb, const int* size3_host, const int* stride3_host, cudaStream_t stream);

@@ -122,6 +122,79 @@ conv_igemm_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __r
   const int gq = lane >> 2, tq = lane & 3;
   const float scale = ep.scale ? *ep.scale : 1.f;
   const bool do_stats = ep.stat_sum != nullptr;
+
+  if (!ep.out_fp32 && (ep.Cout & 7) == 0 && (ep.out_v_stride & 7) == 0 && (ep.out_n_stride & 7) == 0) {
+    // Vector path (every bf16 NDHWC output): the fp32 tile goes through shared memory so that each thread then owns 8
+    // consecutive channels of a voxel -- one 16-byte residual load and one 16-byte store instead of 2-byte / 4-byte
+    // accesses.  Most of these launches (1x1x1 laterals, transposed convs, stride-2 layers at 128^3 / 64^3) are bound by
+    // exactly this traffic.
+    constexpr int OP = BN + 4;                               // padded fp32 row (bank spread)
+    float* so = reinterpret_cast<float*>(smem);
+    __syncthreads();                                         // all warps are done reading the last stage
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = warp_m * 32 + mi * 16 + gq + half * 8;
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+          const int c = warp_n * (BN / 2) + ni * 8 + tq * 2;
+          *reinterpret_cast<float2*>(&so[r * OP + c]) = make_float2(acc[mi][ni][half * 2], acc[mi][ni][half * 2 + 1]);
+        }
+      }
+    __syncthreads();
+    constexpr int CH = BN / 8;                               // 8-channel chunks per row
+    const int ch = tid % CH;
+    const int co = n0 + ch * 8;
+    float bsum[8], bsq[8], bias8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bsum[j] = 0.f; bsq[j] = 0.f; bias8[j] = (ep.bias && co + j < ep.Cout) ? ep.bias[co + j] : 0.f; }
+    if (co < ep.Cout) {
+      for (int r = tid / CH; r < BM; r += THREADS / CH) {
+        const int m = tile * BM + r;
+        if (m >= Lvox) break;
+        const int w_ = m % g.Lw; const int r_ = m / g.Lw; const int h_ = r_ % g.Lh; const int d_ = r_ / g.Lh;
+        const long long pvox = ((long long)(d_ * g.omd + g.ood) * g.Ho + (h_ * g.omh + g.ooh)) * g.Wo + (w_ * g.omw + g.oow);
+        const float4 p0 = *reinterpret_cast<const float4*>(&so[r * OP + ch * 8]);
+        const float4 p1 = *reinterpret_cast<const float4*>(&so[r * OP + ch * 8 + 4]);
+        float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += bias8[j];
+        if (ep.residual) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(ep.residual + ((long long)n * g.Do * g.Ho * g.Wo + pvox) * ep.Cout + co);
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float2 t2 = __bfloat1622float2(hp[k]); v[2 * k] += t2.x; v[2 * k + 1] += t2.y; }
+        }
+        __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          pk[k] = __floats2bfloat162_rn(v[2 * k] * scale, v[2 * k + 1] * scale);
+          const float2 r2 = __bfloat1622float2(pk[k]);       // statistics of the stored tensor
+          bsum[2 * k] += r2.x; bsum[2 * k + 1] += r2.y; bsq[2 * k] += r2.x * r2.x; bsq[2 * k + 1] += r2.y * r2.y;
+        }
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)n * ep.out_n_stride + pvox * ep.out_v_stride + co;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(pk);
+      }
+    }
+    if (do_stats) {
+      __syncthreads();                                       // the tile in shared memory is consumed: reuse it for the sums
+      float* ss = so;                                        // [2][BN]
+      if (tid < 2 * BN) ss[tid] = 0.f;
+      __syncthreads();
+      if (co < ep.Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&ss[ch * 8 + j], bsum[j]); atomicAdd(&ss[BN + ch * 8 + j], bsq[j]); }
+      }
+      __syncthreads();
+      if (tid < BN && n0 + tid < ep.Cout) {
+        atomicAdd(&ep.stat_sum[(size_t)n * ep.Cout + n0 + tid], ss[tid]);
+        atomicAdd(&ep.stat_sq[(size_t)n * ep.Cout + n0 + tid], ss[BN + tid]);
+      }
+    }
+    return;
+  }
+
   float csum[NI][2], csq[NI][2];
 #pragma unroll
   for (int j = 0; j < NI; ++j) { csum[j][0] = csum[j][1] = csq[j][0] = csq[j][1] = 0.f; }
@@ -199,7 +272,8 @@ template <int BN>
 int launch_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
   const int Lvox = g.Ld * g.Lh * g.Lw;
   const int tiles = (Lvox + BM - 1) / BM;
-  const size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2);
+  size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2);
+  if (smem < (size_t)BM * (BN + 4) * 4) smem = (size_t)BM * (BN + 4) * 4;      // fp32 output tile of the vector epilogue
   static bool attr_set = false;
   if (!attr_set) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

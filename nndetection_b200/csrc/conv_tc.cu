@@ -55,6 +55,12 @@ __device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// one lane polls, the warp convenes afterwards: hundreds of polling threads compete with the MMA's shared-memory operand
+// reads (an N = 128 MMA needs the full 128 B/clk)
+__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -147,7 +153,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   const int KC = g.Cin / 32, T = g.T;
 
   if (tid == 0) {
-    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD); mbar_init(EMPTYB(i), MT); }
+    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD / 32); mbar_init(EMPTYB(i), MT); }
     for (int i = 0; i < A_STAGES; ++i) mbar_init(EMPTYA(i), MT);
     for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), MT); mbar_init(TEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -190,17 +196,19 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const int kc = chunk % KC;
       int n, d0, h0, w0, nt;
       decode_tile(tile, n, d0, h0, w0, nt);
-      if (!mbar_test(EMPTYA(astage), a_phase ^ 1)) {
+      const bool a_free = __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(EMPTYA(astage), a_phase ^ 1) : 0, 0) != 0;
+      if (!a_free) {
         // The halo buffer is still being read.  Its release needs the MMAs of the previous chunk, which may be
-        // waiting for weight items whose (deferred) arrival this thread still owes: publish them before blocking.
+        // waiting for weight items whose (deferred) arrival this warp still owes: publish them before blocking.
         cp_async_wait<0>();
         fence_proxy_async();
+        __syncwarp();
         while (pending > 0) {
-          mbar_arrive(FULLB(done_slot));
+          if (lane == 0) mbar_arrive(FULLB(done_slot));
           done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
           --pending;
         }
-        mbar_wait(EMPTYA(astage), a_phase ^ 1);
+        mbar_wait_warp(EMPTYA(astage), a_phase ^ 1, lane);
       }
       const unsigned a_base = smem_u32(sA + astage * A_BYTES);
       const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin + kc * 32;
@@ -227,7 +235,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const int nt = tile % tl.NT;
       const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * 32;
       for (int it = 0; it < NI_ITEMS; ++it) {
-        mbar_wait(EMPTYB(slot), slot_phase ^ 1);
+        mbar_wait_warp(EMPTYB(slot), slot_phase ^ 1, lane);
         if (chunk == 0 && it == 0) load_halo(0);
         if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
         {
@@ -244,7 +252,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
         if (pending > LAG) {
           cp_async_wait<LAG>();
           fence_proxy_async();
-          mbar_arrive(FULLB(done_slot));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(FULLB(done_slot));
           done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
           --pending;
         }
@@ -253,8 +262,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
     }
     cp_async_wait<0>();
     fence_proxy_async();
+    __syncwarp();
     while (pending > 0) {
-      mbar_arrive(FULLB(done_slot));
+      if (lane == 0) mbar_arrive(FULLB(done_slot));
       done_slot = (done_slot + 1 == B_SLOTS) ? 0 : done_slot + 1;
       --pending;
     }
@@ -307,7 +317,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       decode_tile(tile, n, d0, h0, w0, nt);
       const int h = h0 + hy, w = w0 + wx;                    // logical output coordinates
       const bool hw_ok = h < g.Lh && w < g.Lw;
-      mbar_wait(TFULL(acc), acc_phase);
+      mbar_wait_warp(TFULL(acc), acc_phase, lane);
       tc_fence_after();
       // per-warp rows of s_stat accumulate this tile's column sums (lane l owns column c*32 + l of its warp's row)
       if (do_stats) {

@@ -115,7 +115,7 @@ conv_wgrad_tc_kernel(const WtArgs a) {
   // zero the A region once: channel groups beyond Cdy stay zero for the whole kernel (zero MMA rows)
   for (int i = tid; i < STAGES * STAGE_BYTES / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(FULL(i), NPROD); mbar_init(EMPTY(i), 3); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(FULL(i), NPROD / 32); mbar_init(EMPTY(i), 3); }
     mbar_init(DONE, 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,7 +135,8 @@ conv_wgrad_tc_kernel(const WtArgs a) {
     int pending = 0; unsigned done_stage = 0;
     constexpr int LAGW = 2;
     for (int s = 0; s < n_stages; ++s) {
-      mbar_wait(EMPTY(stage), phase ^ 1);
+      if (lane == 0) mbar_wait(EMPTY(stage), phase ^ 1);
+      __syncwarp();
       const unsigned sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
       // A: dy rows  [co group][row][16 voxels]   B: x rows [ci group][row][18 voxels]
       const int a_items = co_groups * ROWS, b_items = B_GROUPS * ROWS;
@@ -174,7 +175,8 @@ conv_wgrad_tc_kernel(const WtArgs a) {
       if (pending > LAGW) {
         cp_async_wait<LAGW>();
         fence_proxy_async();
-        mbar_arrive(FULL(done_stage));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(FULL(done_stage));
         done_stage = (done_stage + 1 == STAGES) ? 0 : done_stage + 1;
         --pending;
       }
@@ -182,8 +184,9 @@ conv_wgrad_tc_kernel(const WtArgs a) {
     }
     cp_async_wait<0>();
     fence_proxy_async();
+    __syncwarp();
     while (pending > 0) {
-      mbar_arrive(FULL(done_stage));
+      if (lane == 0) mbar_arrive(FULL(done_stage));
       done_stage = (done_stage + 1 == STAGES) ? 0 : done_stage + 1;
       --pending;
     }

@@ -95,6 +95,68 @@ def gen_wbc():
          batched_labels=r[2].flatten(), **out)
 
 
+# ------------------------------------------------------------------------------------------ instance transforms (pre_trafo)
+def synth_instances(B, shape, seed, nmax=6):
+    """Random cuboid instances (later ones overwrite earlier ones; ids fully overwritten stay in the mapping)."""
+    rs = np.random.RandomState(seed)
+    t = np.zeros((B, 1) + tuple(shape), dtype=np.float32)
+    maps = []
+    for b in range(B):
+        k = rs.randint(0, nmax + 1)
+        ids = sorted(rs.choice(np.arange(1, 40), size=k, replace=False).tolist())
+        mp = {}
+        for i in ids:
+            lo = [rs.randint(0, s - 3) for s in shape]
+            sz = [rs.randint(1, max(2, s // 3)) for s in shape]
+            sl = tuple(slice(l, min(l + z, s)) for l, z, s in zip(lo, sz, shape))
+            t[b, 0][sl] = i
+            mp[str(i)] = int(rs.randint(0, 3))
+        maps.append(mp)
+    return t, maps
+
+
+TRANSFORM_CASES = [(2, (12, 16, 20), 1), (4, (32, 32, 32), 2), (1, (8, 8, 8), 3), (3, (24, 40, 36), 4)]
+
+
+def gen_transforms():
+    """nndet/io/transforms/instances.py executed from its file with a stand-in for AbstractTransform (the nndet.io package
+    __init__ pulls SimpleITK-dependent modules); the three transforms are chained exactly like the module's pre_trafo."""
+    import importlib.util, types
+    from oracle import transform_oracle as to
+
+    class _AT(torch.nn.Module):
+        def __init__(self, grad=False, **kw):
+            super().__init__(); self.grad = grad
+
+        def __call__(self, **data):
+            return self.forward(**data)
+    base = types.ModuleType("nndet.io.transforms.base"); base.AbstractTransform = _AT
+    for name in ("nndet.io", "nndet.io.transforms"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["nndet.io.transforms.base"] = base
+    spec = importlib.util.spec_from_file_location("ref_inst", os.path.join(ref_import.REF_ROOT, "nndet/io/transforms/instances.py"))
+    ri = importlib.util.module_from_spec(spec); spec.loader.exec_module(ri)
+    out = {}
+    for ci, (B, shape, seed) in enumerate(TRANSFORM_CASES):
+        t, maps = synth_instances(B, shape, seed)
+        data = {"target": torch.from_numpy(t.copy()), "instance_mapping": maps}
+        data = ri.FindInstances(instance_key="target", save_key="present_instances")(**data)
+        data = ri.Instances2Boxes(instance_key="target", map_key="instance_mapping", box_key="boxes", class_key="classes",
+                                  present_instances="present_instances")(**data)
+        data = ri.Instances2Segmentation(instance_key="target", map_key="instance_mapping", present_instances="present_instances")(**data)
+        p, bx, cl, sem = to.pre_trafo(t, maps)
+        for b in range(B):
+            assert np.array_equal(data["present_instances"][b].numpy(), p[b])
+            rb = data["boxes"][b].numpy()
+            assert rb.shape == bx[b].shape and np.array_equal(rb, bx[b])
+            assert np.array_equal(data["classes"][b].numpy(), cl[b])
+            out[f"c{ci}_ids{b}"] = p[b]; out[f"c{ci}_boxes{b}"] = rb; out[f"c{ci}_classes{b}"] = cl[b]
+        assert np.array_equal(data["target"].numpy(), sem)
+        out[f"c{ci}_sem_crc"] = np.asarray([zlib.crc32(sem.tobytes())], dtype=np.int64)
+        out[f"c{ci}_sem_sum"] = np.asarray([sem.sum()], dtype=np.float64)
+    save("transforms", **out)
+
+
 # ------------------------------------------------------------------------------------------ box metrics
 def gen_pairwise():
     g = torch.Generator().manual_seed(11)
@@ -362,7 +424,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -119,3 +119,17 @@ def test_wbc_oracle_matches_reference_fixtures():
     o = bo.batched_wbc(b, s, lab, w, 0.2, ne, 0.02, use_area=True, missing_weight=1.0)
     assert torch.equal(o[0], torch.from_numpy(g["batched_boxes"])) and torch.equal(o[1], torch.from_numpy(g["batched_scores"]))
     assert torch.equal(o[2], torch.from_numpy(g["batched_labels"]))
+
+
+def test_instance_transform_oracle_matches_reference_fixtures():
+    """oracle.transform_oracle.pre_trafo vs the executed FindInstances -> Instances2Boxes -> Instances2Segmentation chain."""
+    import zlib
+    from oracle import transform_oracle as to
+    g = util.golden("transforms")
+    for ci, (B, shape, seed) in enumerate(util.TRANSFORM_CASES):
+        t, maps = util.synth_instances(B, shape, seed)
+        p, bx, cl, sem = to.pre_trafo(t, maps)
+        for b in range(B):
+            assert np.array_equal(p[b], g[f"c{ci}_ids{b}"]) and np.array_equal(cl[b], g[f"c{ci}_classes{b}"])
+            assert bx[b].shape == g[f"c{ci}_boxes{b}"].shape and np.array_equal(bx[b], g[f"c{ci}_boxes{b}"])
+        assert zlib.crc32(sem.tobytes()) == int(g[f"c{ci}_sem_crc"][0])

@@ -54,3 +54,25 @@ def wbc_case(n, seed, extent=60.0):
     weights = torch.rand(n, generator=g) * 0.9 + 0.1
     n_exp = torch.randint(1, 9, (n,), generator=g).float()
     return boxes, scores, weights, n_exp
+
+
+TRANSFORM_CASES = [(2, (12, 16, 20), 1), (4, (32, 32, 32), 2), (1, (8, 8, 8), 3), (3, (24, 40, 36), 4)]
+
+
+def synth_instances(B, shape, seed, nmax=6):
+    """Same generator as scripts/gen_golden.py:synth_instances."""
+    rs = np.random.RandomState(seed)
+    t = np.zeros((B, 1) + tuple(shape), dtype=np.float32)
+    maps = []
+    for b in range(B):
+        k = rs.randint(0, nmax + 1)
+        ids = sorted(rs.choice(np.arange(1, 40), size=k, replace=False).tolist())
+        mp = {}
+        for i in ids:
+            lo = [rs.randint(0, s - 3) for s in shape]
+            sz = [rs.randint(1, max(2, s // 3)) for s in shape]
+            sl = tuple(slice(l, min(l + z, s)) for l, z, s in zip(lo, sz, shape))
+            t[b, 0][sl] = i
+            mp[str(i)] = int(rs.randint(0, 3))
+        maps.append(mp)
+    return t, maps
