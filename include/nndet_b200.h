@@ -37,6 +37,10 @@ int nnd_nms3d_f32(const float* boxes, const float* scores, long long n, float io
                   long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 int nnd_nms2d_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long* keep_out,
                   long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
+/* prefix variant for `keep[:detections_per_img]` (nndet/core/retina.py:376-378): the scan stops once max_keep boxes survived;
+ * keep_out[0 .. min(*n_keep_out, max_keep)) equals the prefix of the full result. */
+int nnd_nms3d_topk_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long max_keep,
+                       long long* keep_out, long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
 /* ---- weighted box clustering.  Replaces wbc + compute_cluster_consolidation, nndet/inference/detection/wbc.py:94-198
  *      (N x N IoU matrix + python while loop with torch.where per cluster).  boxes [n, 6], scores / weights / n_exp_preds [n];
@@ -131,6 +135,7 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
 int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom_host, int Cout, void* out, float* stat_sum,
                              float* stat_sq, cudaStream_t stream);
 int nnd_conv_first_wgrad_f32(const float* x, const void* dy, const int* geom_host, int Cout, float* dw, cudaStream_t stream);
+void nnd_conv_set_tc_ring(int deep);                 /* A/B switch: deeper weight ring in the 128-channel tile kernel (default 1) */
 void nnd_conv_set_first_layer_mma(int enable);       /* A/B switch: tensor-core image layer (default) vs scalar kernels */
 /* fp32 master weight ([Cout][Cin][T], or [Cin][Cout][T] if transposed) -> bf16 fprop / dgrad operands */
 int nnd_pack_weights(const float* w, int Cout, int Cin, int T, int transposed, void* fwd, int CoutPadF, int CinPadF, void* bwd,

@@ -22,6 +22,7 @@ class AnchorGenerator3DS(torch.nn.Module):
         assert len(self.width) == len(self.height) == len(self.depth)
         self.cell_anchors = None
         self._cache = {}
+        self._by_image = {}
         self.num_anchors_per_level: List[int] = None
 
     @staticmethod
@@ -52,7 +53,13 @@ class AnchorGenerator3DS(torch.nn.Module):
             per_fm, per_level = self.grid_anchors(grid_sizes, strides)
             self._cache[key] = (torch.cat(per_fm), per_level)
         anchors, self.num_anchors_per_level = self._cache[key]
+        self._by_image[(tuple(int(v) for v in image_size), str(feature_maps[0].device))] = self._cache[key]
         return [anchors] * image_list.shape[0]
+
+    def lookup(self, image_list: Tensor):
+        """(anchors, anchors per level) of an image shape seen before, else None -- lets the caller start target
+        assignment (which needs only anchors + ground truth) before / beside the network forward."""
+        return self._by_image.get((tuple(int(v) for v in image_list.shape[2:]), str(image_list.device)))
 
     def num_anchors_per_location(self) -> List[int]:
         return [len(w) * len(h) * len(d) for w, h, d in zip(self.width, self.height, self.depth)]

@@ -16,6 +16,16 @@ from torch import Tensor
 from .boxes import engine as E
 
 
+_SIDE_STREAMS = {}          # per device; kept out of the module so that the model stays deep-copyable / picklable
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _HeadLossFn(torch.autograd.Function):
     """DetectionHeadHNMNative.compute_loss (nndet/arch/heads/comb.py:352-405) incl. hard-negative sampling."""
 
@@ -90,14 +100,32 @@ class BaseRetinaNet(nn.Module):
         target_classes: List[Tensor] = targets["target_classes"]
         target_seg: Tensor = targets["target_seg"]
 
-        pred_detection, anchors, pred_seg = self(images)
-        gt = E.GtBatch(target_boxes, target_classes, images.device)
-        a0 = anchors[0]
-        A = a0.shape[0]
-        matches = self.proposal_matcher.match_batch(
-            gt, a0, self.anchor_generator.get_num_acnhors_per_level(),
-            self.anchor_generator.num_anchors_per_location()[0])
-        labels = E.assign_labels(matches, gt, A)
+        # Target assignment needs anchors + ground truth only, not the network outputs: once the anchors of this image
+        # shape are cached it runs on a side stream BESIDE the forward pass (its single-CTA selection kernels would
+        # otherwise sit on the critical path between forward and loss) and is joined before the loss.
+        early = self.anchor_generator.lookup(images) if hasattr(self.anchor_generator, "lookup") else None
+        if early is not None:
+            cur = torch.cuda.current_stream(images.device)
+            side = _side_stream(images.device)
+            side.wait_stream(cur)                     # targets may have been produced / copied on the current stream
+            with torch.cuda.stream(side):
+                gt = E.GtBatch(target_boxes, target_classes, images.device)
+                matches = self.proposal_matcher.match_batch(gt, early[0], early[1],
+                                                            self.anchor_generator.num_anchors_per_location()[0])
+                labels = E.assign_labels(matches, gt, early[0].shape[0])
+            pred_detection, anchors, pred_seg = self(images)
+            cur.wait_stream(side)
+            a0 = anchors[0]
+            A = a0.shape[0]
+        else:
+            pred_detection, anchors, pred_seg = self(images)
+            gt = E.GtBatch(target_boxes, target_classes, images.device)
+            a0 = anchors[0]
+            A = a0.shape[0]
+            matches = self.proposal_matcher.match_batch(
+                gt, a0, self.anchor_generator.get_num_acnhors_per_level(),
+                self.anchor_generator.num_anchors_per_location()[0])
+            labels = E.assign_labels(matches, gt, A)
 
         losses = {}
         reg, cls, pos_idx, neg_idx, counts = _HeadLossFn.apply(

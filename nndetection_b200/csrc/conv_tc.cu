@@ -440,6 +440,9 @@ int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g
 
 }  // namespace
 
+static int g_tc_deep_ring = 1;
+extern "C" void nnd_conv_set_tc_ring(int deep) { g_tc_deep_ring = deep; }
+
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
   if (g.sd != 1 || g.sh != 1 || g.sw != 1) return 0;                       // input position = logical position + offset
   const bool identity = g.omd == 1 && g.omh == 1 && g.omw == 1 && !g.ood && !g.ooh && !g.oow;
@@ -466,8 +469,10 @@ int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom&
     // 4 depth slices share each weight slice (halves the L2 weight traffic); small volumes keep 2-slice tiles so that
     // the persistent grid still has >= one tile per SM
     const long long tiles4 = (long long)g.N * ((g.Ld + 3) / 4) * ((g.Lh + BH - 1) / BH) * ((g.Lw + BW - 1) / BW) * (ep.CoutPad / 128);
-    if (tiles4 >= NND_NUM_SMS) return launch_tc<128, 4, 1, 1, 6>(in, w, g, ep, st);
-    return launch_tc<128, 2, 1, 2, 12>(in, w, g, ep, st);
+    // weight ring depth: the 8 KB weight slices are the latency-bound stream of these layers (L2 -> smem, ~32 KB in flight
+    // per SM with 6 slots); deeper rings keep more bytes in flight (A/B: nnd_conv_set_tc_ring(0) restores 6 / 12)
+    if (tiles4 >= NND_NUM_SMS) return g_tc_deep_ring ? launch_tc<128, 4, 1, 1, 10>(in, w, g, ep, st) : launch_tc<128, 4, 1, 1, 6>(in, w, g, ep, st);
+    return g_tc_deep_ring ? launch_tc<128, 2, 1, 2, 16>(in, w, g, ep, st) : launch_tc<128, 2, 1, 2, 12>(in, w, g, ep, st);
   }
   if (ep.CoutPad % 64 == 0) return g3 ? launch_tc<64, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<64, 4, 1, 2, 12>(in, w, g, ep, st);
   return g3 ? launch_tc<32, 4, 3, 2, 6>(in, w, g, ep, st) : launch_tc<32, 4, 1, 2, 12>(in, w, g, ep, st);

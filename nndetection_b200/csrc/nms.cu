@@ -136,7 +136,7 @@ template <bool CLUSTER>
 __global__ void __launch_bounds__(SCAN_THREADS)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n, int col_blocks,
                 int* __restrict__ kept_rows, long long* __restrict__ keep_out, long long* __restrict__ n_keep_out,
-                int* __restrict__ head_of, int* __restrict__ pos_of) {
+                int* __restrict__ head_of, int* __restrict__ pos_of, int max_keep) {
   extern __shared__ __align__(16) unsigned long long sm_scan[];
   unsigned long long* remv = sm_scan;                                   // [col_blocks]
   unsigned long long* panel = sm_scan + ((col_blocks + 1) & ~1);        // 2 stages x [64][SCAN_WC]
@@ -217,6 +217,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       const int cnt = min(n - base, TILE);
       asm volatile("cp.async.wait_group 1;\n" ::);
       __syncthreads();
+      if (s_count >= max_keep) break;                // the caller only wants the first max_keep survivors (score order)
       const unsigned long long* pn = panel + (size_t)(b & 1) * TILE * SCAN_WC;
       if (tid == 0) {
         // greedy resolution inside the block: only boxes that survive are visited (each visit = one dependent shared-
@@ -287,6 +288,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
+    if (s_count >= max_keep) break;
   }
   __syncthreads();
   if (tid == 0) *n_keep_out = (long long)s_count;
@@ -326,7 +328,8 @@ struct ClusterOut { int* head_of; int* pos_of; };
 
 template <int DIM>
 int nms_impl(const float* boxes, const float* scores, long long n, float thr, long long* keep_out,
-             long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream, const ClusterOut* cl = nullptr) {
+             long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream, const ClusterOut* cl = nullptr,
+             long long max_keep = -1) {
   if (n < 0 || !n_keep_out) return NND_ERR_ARG;
   if (n == 0) {
     NND_CUDA_TRY(cudaMemsetAsync(n_keep_out, 0, sizeof(long long), stream));
@@ -358,8 +361,9 @@ int nms_impl(const float* boxes, const float* scores, long long n, float thr, lo
     scan_attr = true;
   }
   // idx_in (the iota input of the sort) is dead by now: reuse it for the sorted-row numbers of the kept boxes
-  if (cl) nms_scan_kernel<true><<<1, SCAN_THREADS, scan_smem, stream>>>(w.mask, w.idx_out, ni, col_blocks, w.idx_in, keep_out, n_keep_out, cl->head_of, cl->pos_of);
-  else nms_scan_kernel<false><<<1, SCAN_THREADS, scan_smem, stream>>>(w.mask, w.idx_out, ni, col_blocks, w.idx_in, keep_out, n_keep_out, nullptr, nullptr);
+  const int mk = (max_keep < 0 || max_keep > n) ? ni : (int)max_keep;
+  if (cl) nms_scan_kernel<true><<<1, SCAN_THREADS, scan_smem, stream>>>(w.mask, w.idx_out, ni, col_blocks, w.idx_in, keep_out, n_keep_out, cl->head_of, cl->pos_of, ni);
+  else nms_scan_kernel<false><<<1, SCAN_THREADS, scan_smem, stream>>>(w.mask, w.idx_out, ni, col_blocks, w.idx_in, keep_out, n_keep_out, nullptr, nullptr, mk);
   NND_LAUNCH_CHECK("nms_scan_kernel");
   return NND_OK;
 }
@@ -506,6 +510,14 @@ int nnd_nms3d_f32(const float* boxes, const float* scores, long long n, float io
 int nnd_nms2d_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long* keep_out,
                   long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
   return nms_impl<2>(boxes, scores, n, iou_threshold, keep_out, n_keep_out, ws, ws_bytes, stream);
+}
+
+// Same as nnd_nms3d_f32 when only the first `max_keep` survivors (in score order) are consumed -- `keep[:detections_per_img]`
+// after batched_nms, nndet/core/retina.py:376-378: the greedy scan stops at the end of the 64-box block in which the
+// max_keep-th survivor was found; keep_out[0 .. min(*n_keep_out, max_keep)) is identical to the full result's prefix.
+int nnd_nms3d_topk_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long max_keep,
+                       long long* keep_out, long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return nms_impl<3>(boxes, scores, n, iou_threshold, keep_out, n_keep_out, ws, ws_bytes, stream, nullptr, max_keep);
 }
 
 }  // extern "C"

@@ -13,6 +13,8 @@
 #include <math_constants.h>
 
 extern "C" size_t nnd_nms_workspace_bytes(long long n, int dim);
+extern "C" int nnd_nms3d_topk_f32(const float* boxes, const float* scores, long long n, float iou_threshold, long long max_keep,
+                                  long long* keep_out, long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 extern "C" int nnd_nms3d_f32(const float* boxes, const float* scores, long long n, float iou_threshold,
                              long long* keep_out, long long* n_keep_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
@@ -246,7 +248,7 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
     post_filter_kernel<<<1, 1024, 0, s>>>(w.keys_sorted, k, boxes + (size_t)b * A * 6, C, score_thresh, use_score_thresh,
                                           min_size, use_min_size, w.cand_boxes, w.nms_boxes, w.scores, w.labels, w.m);
     NND_LAUNCH_CHECK("post_filter_kernel");
-    rc = nnd_nms3d_f32(w.nms_boxes, w.scores, k, nms_thresh, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, s);
+    rc = nnd_nms3d_topk_f32(w.nms_boxes, w.scores, k, nms_thresh, det_per_img, w.keep, w.n_keep, w.nms_ws, w.nms_bytes, s);
     if (rc != NND_OK) return rc;
     post_gather_kernel<<<1, 128, 0, s>>>(w.keep, w.n_keep, w.m, w.cand_boxes, w.scores, w.labels, det_per_img,
                                          out_boxes + (size_t)b * det_per_img * 6, out_scores + (size_t)b * det_per_img,

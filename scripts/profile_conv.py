@@ -14,6 +14,10 @@ if len(sys.argv) > 6:
 if os.environ.get("NND_STREAM"):                      # "mode,issuers" e.g. NND_STREAM=0,2 disables the streaming kernel
     m_, i_ = (int(v) for v in os.environ["NND_STREAM"].split(","))
     ops.set_stream_path(m_, i_)
+if os.environ.get("NND_TC_RING"):
+    from nndetection_b200 import _lib as L2
+    from ctypes import c_int as _ci
+    L2.lib().nnd_conv_set_tc_ring(_ci(int(os.environ["NND_TC_RING"])))
 dev = torch.device("cuda")
 layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
 x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)

@@ -418,3 +418,56 @@ def test_image_layer_tensor_core_vs_scalar_kernels(cin, shape):
         L.lib().nnd_conv_set_first_layer_mma(c_int(1))
     assert rel_err(res[1][0], res[0][0]) < 5e-3
     assert rel_err(res[1][1], res[0][1]) < 1e-2
+
+
+@pytest.mark.parametrize("name", ["luna", "adam", "lidc", "infer160"])
+def test_full_size_configs_properties(name):
+    """BASELINE.json configs 2, 5, 3, 4 at FULL size (the CPU oracle needs minutes there): size-independent properties.
+    (a) the whole forward through the tcgen05 kernels (streaming z-window, tile kernel, stacked wgrad ...) equals the
+    forward through the mma.sync kernels up to bf16 re-rounding; (b) one full train step gives finite losses, and its
+    detections are clipped to the patch, score-sorted, at most 100 per image and NMS-idempotent; (c) anchors per image
+    match the closed form (1 010 880 for 128^3, 3 411 720 for 96x192x192, 1 974 375 for 160^3)."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.configs import make_plan, synth_batch
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    from nndetection_b200.training import Trainer
+    from nndetection_b200 import _C
+    arch, anc, patch, bs = make_plan(name)
+    if name == "infer160":
+        bs = 1
+    torch.manual_seed(5)
+    net = RetinaUNetV001.from_config_plan(None, arch, anc).cuda()
+    images, targets = synth_batch(patch, bs, arch["in_channels"], arch["classifier_classes"], 21)
+    x = images.cuda()
+    outs = {}
+    try:
+        with torch.no_grad():
+            for mode in ("tc", "mma"):
+                ops.set_tensor_path(mode == "tc")
+                pd, anchors, ps = net(x)
+                outs[mode] = (pd["box_logits"].float().clone(), pd["box_deltas"].float().clone(), ps["seg_logits"].float().clone())
+    finally:
+        ops.set_tensor_path(True)
+    A = {"luna": 1010880, "adam": 1010880, "lidc": 3411720, "infer160": 1974375}[name]
+    assert anchors[0].shape == (A, 6) and outs["tc"][0].shape[0] == bs * A
+    for a, b in zip(outs["tc"], outs["mma"]):
+        assert torch.isfinite(a).all() and rel_err(a, b) < 3e-2
+    if name == "infer160":
+        pred = net.inference_step(x)
+    else:
+        tg = {"target_boxes": [b.cuda() for b in targets["target_boxes"]], "target_classes": [c.cuda() for c in targets["target_classes"]],
+              "target_seg": targets["target_seg"].cuda()}
+        losses, pred = Trainer(net).train_step(x, tg, evaluation=True)
+        for k, v in losses.items():
+            assert torch.isfinite(v).all(), k
+    for i in range(bs):
+        b, sc, lb = pred["pred_boxes"][i], pred["pred_scores"][i], pred["pred_labels"][i]
+        assert b.shape[0] <= 100 and b.shape[0] == sc.shape[0] == lb.shape[0]
+        if b.shape[0] == 0:
+            continue
+        assert (sc[:-1] >= sc[1:]).all() and (lb >= 0).all() and (lb < arch["classifier_classes"]).all()
+        lim = torch.tensor([patch[0], patch[1], patch[0], patch[1], patch[2], patch[2]], device=b.device, dtype=b.dtype)
+        assert (b >= 0).all() and (b <= lim).all()
+        off = lb.to(b) * (b.max() + 1)
+        keep = _C.nms(b + off[:, None], sc, net.nms_thresh)
+        assert torch.equal(keep.cpu(), torch.arange(b.shape[0]))

@@ -78,3 +78,23 @@ def test_idempotent_and_sorted_property_100k():
     iou = bo.box_iou(sub, sub)
     iou.fill_diagonal_(0)
     assert float(iou.max()) <= 0.1
+
+
+@pytest.mark.parametrize("n,thr,mk", [(10000, 0.6, 100), (10000, 0.1, 100), (3000, 0.5, 1), (20000, 0.3, 2500)])
+def test_prefix_variant_equals_prefix_of_full_result(n, thr, mk):
+    """nnd_nms3d_topk_f32 (early-exit scan used by the detection post-processing for keep[:detections_per_img])."""
+    from ctypes import c_float, c_longlong, c_size_t
+    from nndetection_b200 import _lib as L
+    boxes, scores = util.nms_case(n)
+    full = _nms(boxes, scores, thr)
+    lib = L.lib()
+    b, s = boxes.cuda().contiguous(), scores.cuda().contiguous()
+    ws_bytes = lib.nnd_nms_workspace_bytes(n, 3)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    keep = torch.full((n,), -1, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.check(lib.nnd_nms3d_topk_f32(L.ptr(b), L.ptr(s), c_longlong(n), c_float(thr), c_longlong(mk), L.ptr(keep), L.ptr(cnt),
+                                   L.ptr(ws), c_size_t(ws_bytes), L.stream_ptr()), "nnd_nms3d_topk_f32")
+    k = min(int(cnt.item()), mk)
+    assert k == min(mk, full.numel())
+    assert torch.equal(keep[:k].cpu(), full[:k])
