@@ -72,6 +72,18 @@ class NormParams(nn.Module):
             self.register_parameter("bias", None)
 
 
+def _grad_target(param, shape, dev):
+    """Where a parameter-gradient kernel accumulates (all of them ADD into their destination).  When the parameter already
+    owns a dense fp32 `.grad` (the Trainer's flat gradient buffer, zeroed once per step) the kernels add straight into it
+    and autograd gets `None` for that input -- no zero-fill, no temporary and no accumulate kernel per parameter
+    (~220 tiny launches per step).  Otherwise a zeroed temporary is returned through autograd as usual."""
+    g = getattr(param, "grad", None) if param is not None else None
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == tuple(shape) and g.device == dev:
+        return g, None
+    t = torch.zeros(shape, dtype=torch.float32, device=dev)
+    return t, t
+
+
 class _ConvBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, residual, layer):
@@ -126,19 +138,20 @@ class _ConvBlockFn(torch.autograd.Function):
             x, weight, gamma, y, a, b, mean, rstd = ctx.saved_tensors
             dy = ops.empty_cl(N, cout, plan.out_sp, device=dev)
             affine = gamma is not None
+            beta_p = layer.norm.bias if affine else None
             if affine:
-                dgamma = torch.zeros(cout, dtype=torch.float32, device=dev)
-                dbeta = torch.zeros(cout, dtype=torch.float32, device=dev)
+                dgamma, dgamma_ret = _grad_target(gamma, (cout,), dev)
+                dbeta, dbeta_ret = _grad_target(beta_p, (cout,), dev)
             ops.norm_backward(dz, y, a, b, mean, rstd, gamma.detach() if affine else None, N, V, cout, layer.norm.cpg,
                               layer.has_act, dy, dgamma, dbeta)
         else:
             x, weight, gamma = ctx.saved_tensors
             dy = dz
-        dbias = None
+        dbias_ret = None
         if ctx.has_bias:
-            dbias = torch.zeros(cout, dtype=torch.float32, device=dev)
+            dbias, dbias_ret = _grad_target(conv.bias, (cout,), dev)
             ops.channel_sum(dy, N * V, cout, cout, dbias)
-        dw = torch.zeros_like(weight, dtype=torch.float32)
+        dw, dw_ret = _grad_target(weight, tuple(weight.shape), dev)
         T = plan.T
         if layer.is_first:
             ops.conv_first_wgrad(x, dy, plan.fprop[0], cout, dw)
@@ -153,7 +166,9 @@ class _ConvBlockFn(torch.autograd.Function):
             for g in plan.dgrad:
                 ops.conv_gather(dy, wp_b, g, dx, cin, pad32(cin))
         dres = dy if ctx.has_res else None
-        return dx, dw, dbias, dgamma, dbeta, dres, None
+        if has_norm and gamma is not None:
+            dgamma, dbeta = dgamma_ret, dbeta_ret
+        return dx, dw_ret, dbias_ret, dgamma, dbeta, dres, None
 
 
 class BaseConvNormAct(nn.Module):

@@ -177,3 +177,4 @@ def set_tensor_path(enable_tcgen05: bool):
 def set_stream_path(mode: int = 1, issuers: int = 2):
     """0: off, 1: streaming z-window tcgen05 kernel where profitable (default), 2: wherever the shape is supported."""
     L.lib().nnd_conv_set_stream_path(c_int(mode), c_int(issuers))
+

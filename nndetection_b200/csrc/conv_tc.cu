@@ -440,7 +440,7 @@ int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g
 
 }  // namespace
 
-static int g_tc_deep_ring = 1;
+static int g_tc_deep_ring = 2;      // 0: 6 / 12 slots of one tap, 1: 10 / 16 slots, 2 (default): three taps per item
 extern "C" void nnd_conv_set_tc_ring(int deep) { g_tc_deep_ring = deep; }
 
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
@@ -471,6 +471,12 @@ int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom&
     const long long tiles4 = (long long)g.N * ((g.Ld + 3) / 4) * ((g.Lh + BH - 1) / BH) * ((g.Lw + BW - 1) / BW) * (ep.CoutPad / 128);
     // weight ring depth: the 8 KB weight slices are the latency-bound stream of these layers (L2 -> smem, ~32 KB in flight
     // per SM with 6 slots); deeper rings keep more bytes in flight (A/B: nnd_conv_set_tc_ring(0) restores 6 / 12)
+    // mode 2: three taps per pipeline item (24 KB): the producers' per-item bookkeeping (barrier wait, commit, wait_group,
+    // fence, arrive: ~400 cycles) bounds the weight stream at ~40 GB/s per SM with 8 KB items
+    if (g_tc_deep_ring == 2 && g3) {
+      if (tiles4 >= NND_NUM_SMS) return launch_tc<128, 4, 3, 1, 3>(in, w, g, ep, st);
+      return launch_tc<128, 2, 3, 2, 4>(in, w, g, ep, st);
+    }
     if (tiles4 >= NND_NUM_SMS) return g_tc_deep_ring ? launch_tc<128, 4, 1, 1, 10>(in, w, g, ep, st) : launch_tc<128, 4, 1, 1, 6>(in, w, g, ep, st);
     return g_tc_deep_ring ? launch_tc<128, 2, 1, 2, 16>(in, w, g, ep, st) : launch_tc<128, 2, 1, 2, 12>(in, w, g, ep, st);
   }

@@ -140,6 +140,9 @@ __device__ __forceinline__ Item decode_item(int idx, const TcsTiles& tl, int D) 
 }
 
 // A_SLOTS input slices in the ring, of which LAG + 1 may still be in flight (published LAG slices late)
+// (scripts/mma_rate.cu modes 2 / 3: the 160-byte row pitch of the halo and the 16-byte dx shifts, which put most 8 x 16 B core
+// matrices across two 128-byte shared-memory lines, cost nothing per MMA -- 56.0 cycles at N = 96 either way -- so there is
+// no aligned-copy variant of the halo.)
 template <int CIN, int NI, int A_SLOTS, int LAG, bool STATS>
 __global__ void __launch_bounds__((4 + NI + 4) * 32, 1)
 conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,

@@ -72,6 +72,39 @@ __global__ void channel_sum_kernel(const T* __restrict__ src, long long rows, in
   for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out[c], sh[c] * scale);
 }
 
+// bf16 fast path (C % 8 == 0, stride % 8 == 0): a thread owns one 8-channel chunk, 16-byte loads, 4 rows in flight
+__global__ void __launch_bounds__(256)
+channel_sum_bf16x8_kernel(const uint4* __restrict__ src, long long rows, int C8, long long stride8, int rows_per_block, float scale,
+                          float* __restrict__ out) {
+  extern __shared__ float sh[];          // [C8 * 8]
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) sh[c] = 0.f;
+  __syncthreads();
+  const int rpb = blockDim.x / C8;
+  const int cc = threadIdx.x % C8, rr = threadIdx.x / C8;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(r0 + (long long)rows_per_block, rows);
+  if (rr < rpb) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long r = r0 + rr; r < r1; r += 4 * rpb) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (r + u * rpb < r1) v[u] = src[(r + u * rpb) * stride8 + cc];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * rpb >= r1) break;
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(h[k]); acc[2 * k] += t.x; acc[2 * k + 1] += t.y; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[cc * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C8 * 8; c += blockDim.x) atomicAdd(&out[c], sh[c] * scale);
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __float2bfloat16(s[i]);
@@ -136,7 +169,10 @@ int nnd_channel_sum(const void* src, int is_bf16, long long rows, int C, long lo
   int rpb = 4096;
   while (rpb > 64 && (rows + rpb - 1) / rpb < NND_NUM_SMS * 2) rpb >>= 1;
   const unsigned blocks = (unsigned)((rows + rpb - 1) / rpb);
-  if (is_bf16) channel_sum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>((const __nv_bfloat16*)src, rows, C, stride, rpb, scale, out);
+  if (is_bf16 && C % 8 == 0 && stride % 8 == 0 && C / 8 <= 256 && ((size_t)src & 15) == 0) {
+    const int C8 = C / 8, threads = (256 / C8) * C8;
+    channel_sum_bf16x8_kernel<<<blocks, threads, C * sizeof(float), st>>>((const uint4*)src, rows, C8, stride / 8, rpb, scale, out);
+  } else if (is_bf16) channel_sum_kernel<__nv_bfloat16><<<blocks, 256, C * sizeof(float), st>>>((const __nv_bfloat16*)src, rows, C, stride, rpb, scale, out);
   else channel_sum_kernel<float><<<blocks, 256, C * sizeof(float), st>>>((const float*)src, rows, C, stride, rpb, scale, out);
   NND_LAUNCH_CHECK("channel_sum_kernel");
   return NND_OK;

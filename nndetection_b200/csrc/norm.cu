@@ -46,26 +46,38 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
-// z = relu?(a[n,c] * y + b[n,c]);  one thread = 8 channels of one voxel
-__global__ void norm_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
-                                  long long per_sample8, int C8, long long total8, int relu, uint4* __restrict__ z) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int n = (int)(i / per_sample8);
-  const int c = (int)(i % C8) * 8;
-  float f[8];
-  unpack8(y[i], f);
-  const float4* ap = reinterpret_cast<const float4*>(a + (size_t)n * C8 * 8 + c);
-  const float4* bp = reinterpret_cast<const float4*>(b + (size_t)n * C8 * 8 + c);
-  const float4 a0 = ap[0], a1 = ap[1], b0 = bp[0], b1 = bp[1];
-  const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-  const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+// z = relu?(a[n,c] * y + b[n,c]).  grid (chunks, N); a thread owns ONE 8-channel chunk (its 16 scale/shift values stay in
+// registers) and walks the voxels of its block's range with 4 independent 16-byte loads in flight -- no per-element
+// parameter loads, no 64-bit divisions (this pass is pure HBM streaming: 2 * C bytes read + written per voxel).
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ a, const float* __restrict__ b,
+                  int V, int C8, int rows, int vox_per_block, int relu, uint4* __restrict__ z) {
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % C8, rr = threadIdx.x / C8;
+  if (rr >= rows) return;
+  const int C = C8 * 8;
+  float av[8], bv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float t = fmaf(av[j], f[j], bv[j]);
-    f[j] = relu ? fmaxf(t, 0.f) : t;
+  for (int j = 0; j < 8; ++j) { av[j] = a[n * C + cc * 8 + j]; bv[j] = b[n * C + cc * 8 + j]; }
+  const int v0 = blockIdx.x * vox_per_block, v1 = min(v0 + vox_per_block, V);
+  const size_t base = (size_t)n * V * C8 + cc;
+  for (int v = v0 + rr; v < v1; v += 4 * rows) {
+    uint4 in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (v + u * rows < v1) in[u] = y[base + (size_t)(v + u * rows) * C8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v + u * rows >= v1) break;
+      float f[8];
+      unpack8(in[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(av[j], f[j], bv[j]);
+        f[j] = relu ? fmaxf(t, 0.f) : t;
+      }
+      z[base + (size_t)(v + u * rows) * C8] = pack8(f);
+    }
   }
-  z[i] = pack8(f);
 }
 
 // S1[n,c] += sum_v g, S2[n,c] += sum_v g * xhat.   grid (chunks, N), block = C8 * rows
@@ -84,16 +96,24 @@ __global__ void norm_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4
     s1[j] = 0.f; s2[j] = 0.f;
   }
   const int v0 = blockIdx.x * vox_per_block, v1 = min(v0 + vox_per_block, V);
-  for (int v = v0 + rr; v < v1; v += rows) {
-    const long long i = ((long long)n * V + v) * C8 + cc;
-    float fy[8], fd[8];
-    unpack8(y[i], fy); unpack8(dz[i], fd);
+  const size_t base = (size_t)n * V * C8 + cc;
+  for (int v = v0 + rr; v < v1; v += 4 * rows) {
+    uint4 iy[4], id[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float pre = fmaf(av[j], fy[j], bv[j]);
-      const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
-      s1[j] += gq;
-      s2[j] += gq * (fy[j] - mv[j]) * rv[j];
+    for (int u = 0; u < 4; ++u)
+      if (v + u * rows < v1) { iy[u] = y[base + (size_t)(v + u * rows) * C8]; id[u] = dz[base + (size_t)(v + u * rows) * C8]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v + u * rows >= v1) break;
+      float fy[8], fd[8];
+      unpack8(iy[u], fy); unpack8(id[u], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(av[j], fy[j], bv[j]);
+        const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
+        s1[j] += gq;
+        s2[j] += gq * (fy[j] - mv[j]) * rv[j];
+      }
     }
   }
 #pragma unroll
@@ -133,25 +153,56 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ S1, const flo
   if (dbeta) atomicAdd(&dbeta[c], S1[n * C + c]);
 }
 
-__global__ void norm_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y,
-                                      const float* __restrict__ a, const float* __restrict__ b,
-                                      const float* __restrict__ k1, const float* __restrict__ k2,
-                                      const float* __restrict__ k3, long long per_sample8, int C8, long long total8,
-                                      int relu, uint4* __restrict__ dy) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int n = (int)(i / per_sample8);
-  const int c = (int)(i % C8) * 8;
-  const size_t o = (size_t)n * C8 * 8 + c;
-  float fy[8], fd[8];
-  unpack8(y[i], fy); unpack8(dz[i], fd);
+// dy = k1 * g + k2 * y + k3 with g = dz * [pre-activation > 0]; same thread mapping as norm_apply_kernel (40 per-channel
+// coefficients in registers, 2 x 4 independent 16-byte loads in flight)
+__global__ void __launch_bounds__(256)
+norm_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, const float* __restrict__ a,
+                      const float* __restrict__ b, const float* __restrict__ k1, const float* __restrict__ k2,
+                      const float* __restrict__ k3, int V, int C8, int rows, int vox_per_block, int relu,
+                      uint4* __restrict__ dy) {
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % C8, rr = threadIdx.x / C8;
+  if (rr >= rows) return;
+  const int C = C8 * 8;
+  float av[8], bv[8], c1[8], c2[8], c3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float pre = fmaf(a[o + j], fy[j], b[o + j]);
-    const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
-    fd[j] = fmaf(k1[o + j], gq, fmaf(k2[o + j], fy[j], k3[o + j]));
+    const int o = n * C + cc * 8 + j;
+    av[j] = a[o]; bv[j] = b[o]; c1[j] = k1[o]; c2[j] = k2[o]; c3[j] = k3[o];
   }
-  dy[i] = pack8(fd);
+  const int v0 = blockIdx.x * vox_per_block, v1 = min(v0 + vox_per_block, V);
+  const size_t base = (size_t)n * V * C8 + cc;
+  for (int v = v0 + rr; v < v1; v += 4 * rows) {
+    uint4 iy[4], id[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * rows < v1) { iy[u] = y[base + (size_t)(v + u * rows) * C8]; id[u] = dz[base + (size_t)(v + u * rows) * C8]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v + u * rows >= v1) break;
+      float fy[8], fd[8];
+      unpack8(iy[u], fy); unpack8(id[u], fd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = fmaf(av[j], fy[j], bv[j]);
+        const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
+        fd[j] = fmaf(c1[j], gq, fmaf(c2[j], fy[j], c3[j]));
+      }
+      dy[base + (size_t)(v + u * rows) * C8] = pack8(fd);
+    }
+  }
+}
+
+// launch shape shared by the streaming passes: grid (voxel chunks, N), block = rows x C8 threads (<= 256)
+struct StreamShape { int rows, threads, vpb; dim3 grid; };
+static StreamShape stream_shape(int N, long long V, int C8) {
+  StreamShape s;
+  s.rows = 256 / C8; if (s.rows < 1) s.rows = 1;
+  s.threads = s.rows * C8;
+  s.vpb = 2048;
+  while (s.vpb > 64 && (V + s.vpb - 1) / s.vpb * N < NND_NUM_SMS * 8) s.vpb >>= 1;
+  s.grid = dim3((unsigned)((V + s.vpb - 1) / s.vpb), (unsigned)N);
+  return s;
 }
 
 }  // namespace
@@ -171,10 +222,10 @@ int nnd_norm_finalize(const float* ssum, const float* ssq, const float* gamma, c
 int nnd_norm_apply(const void* y, const float* a, const float* b, int N, long long V, int C, int relu, void* z,
                    cudaStream_t st) {
   if (C % 8) return NND_ERR_ARG;
-  const long long total8 = (long long)N * V * C / 8;
-  if (total8 == 0) return NND_OK;
-  norm_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>((const uint4*)y, a, b, V * C / 8, C / 8, total8, relu,
-                                                                      (uint4*)z);
+  if ((long long)N * V == 0) return NND_OK;
+  if (C > 2048 || V > 0x7fffffffll) return NND_ERR_ARG;
+  const StreamShape sh = stream_shape(N, V, C / 8);
+  norm_apply_kernel<<<sh.grid, sh.threads, 0, st>>>((const uint4*)y, a, b, (int)V, C / 8, sh.rows, sh.vpb, relu, (uint4*)z);
   NND_LAUNCH_CHECK("norm_apply_kernel");
   return NND_OK;
 }
@@ -200,9 +251,9 @@ int nnd_norm_backward(const void* dz, const void* y, const float* a, const float
   NND_LAUNCH_CHECK("norm_bwd_reduce_kernel");
   norm_bwd_finalize_kernel<<<N, C, 0, st>>>(S1, S2, gamma, mean, rstd, C, cpg, (float)V, k1, k2, k3, dgamma, dbeta);
   NND_LAUNCH_CHECK("norm_bwd_finalize_kernel");
-  const long long total8 = (long long)N * V * C8;
-  norm_bwd_apply_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>((const uint4*)dz, (const uint4*)y, a, b, k1, k2, k3,
-                                                                          V * C8, C8, total8, relu, (uint4*)dy);
+  const StreamShape sh = stream_shape(N, V, C8);
+  norm_bwd_apply_kernel<<<sh.grid, sh.threads, 0, st>>>((const uint4*)dz, (const uint4*)y, a, b, k1, k2, k3, (int)V, C8, sh.rows,
+                                                        sh.vpb, relu, (uint4*)dy);
   NND_LAUNCH_CHECK("norm_bwd_apply_kernel");
   return NND_OK;
 }

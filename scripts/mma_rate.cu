@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(int N, int issuers, int it
     const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
     const unsigned a_base = smem_u32(smem) + uwarp * 8192;
     const unsigned b_base = smem_u32(smem) + 40960 + uwarp * 8192;
-    const unsigned long long a0 = make_desc(a_base, 2048, 128);
+    // mode 2 / 3: A laid out like the convolution halo (8-row groups at a 160-byte pitch, k-groups 2880 B apart); mode 2 keeps
+    // every core matrix inside one 128-byte line (start offsets multiples of 640 B), mode 3 adds the dx tap shifts (16 / 32 B)
+    const unsigned long long a0 = mode >= 2 ? make_desc(a_base, 2880, 160) : make_desc(a_base, 2048, 128);
     const unsigned long long b0 = make_desc(b_base, N * 16, 128);
     const int width = mode == 1 ? N / 3 : N;
     const int span = 512 / issuers;
@@ -72,7 +74,8 @@ __global__ void __launch_bounds__(160, 1) rate_kernel(int N, int issuers, int it
     int col = 0;
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
-      if (elect_one()) tc_mma(cbase + col, a0 + (unsigned long long)((i & 7) * 16), b0, idesc, 1u);
+      const unsigned long long ashift = mode == 3 ? (unsigned long long)(i % 3) : (mode == 2 ? 0ull : (unsigned long long)((i & 7) * 16));
+      if (elect_one()) tc_mma(cbase + col, a0 + ashift, b0, idesc, 1u);
       __syncwarp();
       if (mode == 1) { col += width; if (col + N > span) col = 0; }
     }
@@ -117,10 +120,11 @@ int main() {
   const int Ns[] = {32, 48, 64, 96, 128, 192, 256};
   printf("style mode N issuers cycles_per_mma_per_SM  (ideal 128*N/256 = N/2)\n");
   for (int style = 1; style >= 0; --style)
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 4; ++mode)
     for (int N : Ns)
       for (int issuers : {1, 2, 4}) {
         if (mode == 1 && (N % 48 != 0)) continue;
+        if (mode >= 2 && (style == 0 || (N != 96 && N != 128 && N != 32))) continue;
         if (N > 512 / issuers) continue;
         cudaMemset(d, 0, sizeof(h));
         rate_kernel<<<148, 160, 96 * 1024>>>(N, issuers, iters, mode, style, d);

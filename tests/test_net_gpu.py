@@ -471,3 +471,28 @@ def test_full_size_configs_properties(name):
         off = lb.to(b) * (b.max() + 1)
         keep = _C.nms(b + off[:, None], sc, net.nms_thresh)
         assert torch.equal(keep.cpu(), torch.arange(b.shape[0]))
+
+
+@pytest.mark.parametrize("norm", [True, False])
+def test_direct_gradient_accumulation_equals_autograd_accumulation(norm):
+    """With the Trainer's flat gradient buffer every parameter owns a dense fp32 .grad and the wgrad / bias / norm kernels
+    add straight into it (arch/conv.py:_grad_target); without it the same kernels fill temporaries that autograd
+    accumulates.  Same kernels, same operands: equal up to the order of the fp32 atomics; a second backward accumulates.
+    (Single block: whole-network runs differ run to run by bf16 re-rounding chaos, see grad_err.json.)"""
+    mine, _ = make_pair("instance", 64, 64, 3, 1, norm=norm)
+    g = torch.Generator().manual_seed(61)
+    x = q(torch.randn(2, 64, 8, 16, 16, generator=g)).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    gy = q(torch.randn(2, 64, 8, 16, 16, generator=g)).cuda().to(torch.bfloat16)
+    grads = {}
+    for mode in ("autograd", "direct", "direct_twice"):
+        if mode == "autograd":
+            mine.zero_grad(set_to_none=True)
+        elif mode == "direct":
+            for p_ in mine.parameters():
+                p_.grad = torch.zeros_like(p_, dtype=torch.float32)
+        mine(x.clone().requires_grad_(True)).backward(gy)
+        grads[mode] = {k: p_.grad.detach().clone() for k, p_ in mine.named_parameters()}
+    assert len(grads["autograd"]) == (3 if norm else 2)
+    for k in grads["autograd"]:
+        assert rel_err(grads["direct"][k], grads["autograd"][k]) < 1e-5, k
+        assert rel_err(grads["direct_twice"][k], 2 * grads["autograd"][k]) < 1e-5, k
