@@ -166,6 +166,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # The contract is ONE JSON line on stdout: anything a library prints there while the job runs (NCCL's version banner at
+    # communicator creation, for one) is sent to stderr instead; fd 1 is restored just before the result line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -235,6 +240,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
 
     if args.profile:
+        sys.stdout.flush(); os.dup2(saved_stdout, 1)
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}), flush=True)
         return
@@ -285,7 +291,9 @@ def main():
                 out["cpu_baseline"] = cpu_baseline()
             except Exception as e:                       # never lose the GPU line to a host-side problem
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+        sys.stdout.flush(); os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
