@@ -123,7 +123,7 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
  *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
  *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel. */
 void nnd_conv_set_tensor_path(int enable_tcgen05);
-void nnd_conv_set_wgrad_tc(int enable);              /* A/B switch: tcgen05 wgrad (default) vs mma.sync halo wgrad */
+void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,

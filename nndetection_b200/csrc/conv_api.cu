@@ -20,6 +20,9 @@ int nnd_conv_wgrad_tc32_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc32_profitable(const ConvGeom& g);
 int nnd_conv_wgrad_tc32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ConvGeom& g, float* dw, long long s_co, long long s_ci,
                         long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_wgrad_tcn_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tcn(const __nv_bfloat16* dy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw, long long s_co,
+                       long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_halo_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_halo(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                         long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
@@ -85,6 +88,11 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g)))
     return nnd_conv_wgrad_tc32((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
+  // g_wgrad_tc: 1 = tcgen05 wgrad kernels (default), 2 = also the stacked 32-channel one on small volumes (tests), 4 = the
+  // all-taps 128-output-channel kernel of conv_wgrad_tcn.cu (opt-in: measured SLOWER than the filter-row kernel, 0.38 vs
+  // 0.23 ms at 32^3 x 4 -- its N = 48 MMAs cost 44 cycles for 24 cycles of math; kept as the A/B record of that experiment)
+  if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx))
+    return nnd_conv_wgrad_tcn((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_tc((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx))

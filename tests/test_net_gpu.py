@@ -496,3 +496,31 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(norm):
     for k in grads["autograd"]:
         assert rel_err(grads["direct"][k], grads["autograd"][k]) < 1e-5, k
         assert rel_err(grads["direct_twice"][k], 2 * grads["autograd"][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("cin,shape", [(128, (2, 8, 16, 16)), (128, (1, 5, 9, 19)), (64, (1, 4, 8, 32)), (256, (1, 2, 4, 16))])
+def test_all_taps_wgrad_128_output_channels(cin, shape):
+    """conv_wgrad_tcn.cu (27 taps of a 16-input-channel class per CTA, dy taps stacked along N; opt-in mode 4 -- correct but
+    slower than the filter-row kernel) against the CPU oracle on bf16-exact operands (5e-3), against the filter-row tcgen05
+    kernel (mode 1) and the mma.sync kernel (mode 0): 1e-3."""
+    from nndetection_b200 import _lib as L
+    from ctypes import c_int
+    mine, ref = make_pair("instance", cin, 128, 3, 1, norm=False)
+    g = torch.Generator().manual_seed(71)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res = {}
+    try:
+        for mode in (4, 1, 0):
+            L.lib().nnd_conv_set_wgrad_tc(c_int(mode))
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            mine(xm).backward(gy.cuda().to(torch.bfloat16))
+            res[mode] = mine.conv.weight.grad.cpu().clone()
+    finally:
+        L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+    assert rel_err(res[4], ref.conv.weight.grad) < 5e-3
+    assert rel_err(res[4], res[1]) < 1e-3 and rel_err(res[4], res[0]) < 1e-3
