@@ -13,6 +13,7 @@
 // CTA = persistent over tiles of 2 (z') x 8 (y) x 16 (x) voxels, 3-stage ring (4 x 8 tiles with 2 stages were slower: 0.87 vs 0.58 ms); 4 producer warps (cp.async, zero fill = padding), 3
 // issuer warps (one per dx tap = independent accumulators), 4 epilogue warps (TMEM -> fp32 atomics into dW once at the end).
 #include "conv_common.cuh"
+#include "tcgen05.cuh"
 
 namespace {
 
@@ -31,59 +32,6 @@ constexpr int STAGES = 3;
 constexpr int NCOL = 3 * C;               // 96 accumulator columns per dx tap
 constexpr int THREADS = (4 + 3 + 4) * 32;
 
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(unsigned bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// descriptors as {lo, hi} words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14 (loop invariant)
-__device__ __forceinline__ void tc_mma2(unsigned tmem_d, unsigned alo, unsigned ahi, unsigned blo, unsigned bhi, unsigned idesc,
-                                        unsigned accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct W32Args {
   const __nv_bfloat16* dy; const __nv_bfloat16* x;
@@ -220,15 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_tc32_kernel(const W32Ar
     } else {
       // ================================================================ epilogue: TMEM -> fp32 atomics into dW
       const int q = warp & 3;                      // TMEM lanes 32q..: row block b = q <-> tz = 1 - q (q = 3: unused rows)
-      if (lane == 0) {                             // one poller per warp, with backoff: the wait lasts the whole kernel
-        unsigned ok = 0;
-        while (!ok) {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                       : "=r"(ok) : "r"(DONE), "r"(0u) : "memory");
-          if (!ok) __nanosleep(2000);
-        }
-      }
-      __syncwarp();
+      mbar_wait_warp_backoff(DONE, 0, lane, 2000);   // the wait lasts the whole kernel
       tc_fence_after();
       if (q < 3) {
         const int tz = 1 - q;
