@@ -51,9 +51,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken inside [t0, t1] (wall clock of the timed region; all samples if none fall inside).
+        The sampler is started BEFORE the warm-up so that nvidia-smi's start-up (driver queries that can stall launches for
+        tens of ms) never lands inside the timed region."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -61,6 +64,8 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [r for t, r in self.rows if t0 is not None and t0 <= t <= t1]
+        self.rows = inside if inside else [r for _, r in self.rows]
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -219,25 +224,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for i in range(args.warmup):
         step_resident(i)
     barrier()
 
     # ---- timed region 1: device-resident inputs
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     l0 = lib.nnd_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_w0 = time.time()
     e0.record()
     for i in range(args.steps):
         step_resident(i)
     e1.record()
     barrier()
+    t_w1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = lib.nnd_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_w0, t_w1) if rank == 0 else None
 
     if args.profile:
         sys.stdout.flush(); os.dup2(saved_stdout, 1)
