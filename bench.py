@@ -195,7 +195,9 @@ def main():
     trainer = Trainer(net, distributed=world > 1)
 
     # ---- synthetic data: 4 distinct batches (> L2: one batch of activations alone is GBs), pinned on the host
-    n_batches = 4
+    # as many distinct batches as warm-up steps (<= 4): every batch's allocation pattern (it depends on the number of ground-truth
+    # boxes) is seen once before the timed region -- a first-time cudaMalloc inside it costs ~10 ms
+    n_batches = max(1, min(4, args.warmup))
     host = []
     for i in range(n_batches):
         im, tg = synth_batch(patch, bs, arch["in_channels"], arch["classifier_classes"], 1234 + 97 * rank + i)
