@@ -9,8 +9,9 @@
 //     taps: smem layout [channel group of 8][z][y][x][8 ch] -- one voxel = one 16-byte core-matrix row, so the UMMA
 //     shared-memory descriptor of tap (dz,dy,dx) is just the halo base + ((dz+1)*18 + (dy+1))*10 + (dx+1) rows:
 //     K-major, no swizzle, SBO = 160 B (halo row pitch), LBO = channel-group pitch.  No im2col, no per-tap reload.
-//   * the weight slice of one (tap, 32-channel chunk) [N_TILE x 32] streams through a 6-slot ring in the canonical
-//     K-major no-swizzle layout [k group][n][8] (SBO 128 B, LBO N_TILE*16 B) and is shared by the MT slice-MMAs.
+//   * the weight slices of TG taps of one 32-channel chunk (TG x [N_TILE x 32]) stream through a ring of pipeline items in
+//     the canonical K-major no-swizzle layout [k group][n][8] (SBO 128 B, LBO N_TILE*16 B) and are shared by the MT
+//     slice-MMAs; three taps per item (24 KB at N_TILE = 128) amortise the producers' per-item bookkeeping.
 //   * accumulators live in TMEM: MT x N_TILE fp32 columns, double buffered so the epilogue of tile i overlaps the
 //     MMAs of tile i+1.
 // Roles: warps 0-3 producers (cp.async 16-byte gathers with zero fill = padding; completion ->
