@@ -1,0 +1,116 @@
+"""Host logic of the convolution family, checked on CPU: the geometry tables `ConvPlan` hands to the gather-convolution
+kernels (csrc/conv_common.cuh: out[n, lo*om + oo, co] = sum_taps sum_ci in[n, lo*s + off_tap, ci] * W[tap_w][co][ci]) are
+emulated in numpy and compared with torch's Conv3d / ConvTranspose3d forward and input-gradient on small shapes -- every
+(kernel, stride, transposed) form the Retina U-Net uses, incl. the parity-class decomposition of the strided dgrad."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from nndetection_b200.arch.conv_ops import ConvPlan
+
+
+def _emulate(geom, x, w_taps, cout):
+    """x [N, Di, Hi, Wi, Cin] (NDHWC), w_taps[tap] = [cout, cin] matrix; returns (out [N, Do, Ho, Wo, cout] with untouched voxels NaN)."""
+    a = list(geom)
+    N, Di, Hi, Wi, Cin = a[0:5]
+    L = a[5:8]; s = a[8:11]; Do, Ho, Wo = a[11:14]; om = a[14:17]; oo = a[17:20]; T = a[20]
+    taps = [a[21 + 4 * t: 25 + 4 * t] for t in range(T)]
+    out = np.full((N, Do, Ho, Wo, cout), np.nan, dtype=np.float64)
+    for n in range(N):
+        for ld, lh, lw in itertools.product(range(L[0]), range(L[1]), range(L[2])):
+            acc = np.zeros(cout)
+            for od, oh, ow, tw in taps:
+                i = (ld * s[0] + od, lh * s[1] + oh, lw * s[2] + ow)
+                if 0 <= i[0] < Di and 0 <= i[1] < Hi and 0 <= i[2] < Wi:
+                    acc += w_taps[tw] @ x[n, i[0], i[1], i[2]]
+            out[n, ld * om[0] + oo[0], lh * om[1] + oo[1], lw * om[2] + oo[2]] = acc
+    return out
+
+
+CASES = [((3, 3, 3), (1, 1, 1), False), ((3, 3, 3), (2, 2, 2), False), ((1, 3, 3), (1, 2, 2), False), ((1, 1, 1), (1, 1, 1), False),
+         ((2, 2, 2), (2, 2, 2), True), ((1, 2, 2), (1, 2, 2), True)]
+
+
+@pytest.mark.parametrize("k,s,transposed", CASES)
+def test_plan_geometry_reproduces_torch_conv_forward_and_dgrad(k, s, transposed):
+    rs = np.random.RandomState(0)
+    N, cin, cout, sp = 1, 3, 2, (5, 6, 4)
+    p = (0, 0, 0) if transposed else tuple((kk - 1) // 2 for kk in k)
+    x = rs.standard_normal((N, cin) + sp)
+    T = k[0] * k[1] * k[2]
+    plan = ConvPlan(N, cin, cout, sp, k, s, p, transposed)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    if transposed:
+        w = rs.standard_normal((cin, cout) + k)
+        y = F.conv_transpose3d(xt, torch.from_numpy(w), stride=s)
+        w_f = [w[:, :, a, b, c].T for a, b, c in itertools.product(*[range(v) for v in k])]       # [cout, cin] per tap
+        w_b = [w[:, :, a, b, c] for a, b, c in itertools.product(*[range(v) for v in k])]         # dgrad: [cin, cout]
+    else:
+        w = rs.standard_normal((cout, cin) + k)
+        y = F.conv3d(xt, torch.from_numpy(w), stride=s, padding=p)
+        w_f = [w[:, :, a, b, c] for a, b, c in itertools.product(*[range(v) for v in k])]
+        w_b = [w[:, :, a, b, c].T for a, b, c in itertools.product(*[range(v) for v in k])]
+    assert tuple(y.shape[2:]) == plan.out_sp and len(w_f) == T
+    # forward: the union of the launches writes every output voxel exactly once
+    xn = np.transpose(x, (0, 2, 3, 4, 1))
+    out = np.full((N,) + plan.out_sp + (cout,), np.nan)
+    for g in plan.fprop:
+        o = _emulate(g, xn, w_f, cout)
+        m = ~np.isnan(o)
+        assert np.isnan(out[m]).all()
+        out[m] = o[m]
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(out, np.transpose(y.detach().numpy(), (0, 2, 3, 4, 1)), rtol=1e-10, atol=1e-10)
+    # input gradient: parity classes of the strided conv / the k = s conv of the transposed conv
+    gy = rs.standard_normal(tuple(y.shape))
+    y.backward(torch.from_numpy(gy))
+    gyn = np.transpose(gy, (0, 2, 3, 4, 1))
+    dx = np.full((N,) + sp + (cin,), np.nan)
+    for g in plan.dgrad:
+        o = _emulate(g, gyn, w_b, cin)
+        m = ~np.isnan(o)
+        assert np.isnan(dx[m]).all()
+        dx[m] = o[m]
+    if plan.dgrad_covers_all:
+        assert not np.isnan(dx).any()
+    dx = np.nan_to_num(dx, nan=0.0)              # voxels no launch writes receive no gradient (zero-filled by the caller)
+    np.testing.assert_allclose(dx, np.transpose(xt.grad.numpy(), (0, 2, 3, 4, 1)), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("k,s,transposed", CASES)
+def test_plan_geometry_reproduces_torch_weight_gradient(k, s, transposed):
+    """dW[tap][co][ci] = sum_lo dy[lo*om + oo][co] * x[lo*s + off_tap][ci] over the plan's wgrad launches (csrc/conv_wgrad*.cu)."""
+    rs = np.random.RandomState(1)
+    N, cin, cout, sp = 2, 3, 2, (4, 5, 6)
+    p = (0, 0, 0) if transposed else tuple((kk - 1) // 2 for kk in k)
+    x = rs.standard_normal((N, cin) + sp)
+    plan = ConvPlan(N, cin, cout, sp, k, s, p, transposed)
+    xt = torch.from_numpy(x)
+    if transposed:
+        w = torch.from_numpy(rs.standard_normal((cin, cout) + k)).requires_grad_(True)
+        y = F.conv_transpose3d(xt, w, stride=s)
+    else:
+        w = torch.from_numpy(rs.standard_normal((cout, cin) + k)).requires_grad_(True)
+        y = F.conv3d(xt, w, stride=s, padding=p)
+    gy = rs.standard_normal(tuple(y.shape))
+    y.backward(torch.from_numpy(gy))
+    xn, gyn = np.transpose(x, (0, 2, 3, 4, 1)), np.transpose(gy, (0, 2, 3, 4, 1))
+    T = k[0] * k[1] * k[2]
+    dw = np.zeros((T, cout, cin))
+    for g in plan.wgrad:
+        a = list(g)
+        Di, Hi, Wi = a[1:4]; L = a[5:8]; st = a[8:11]; om = a[14:17]; oo = a[17:20]
+        taps = [a[21 + 4 * t: 25 + 4 * t] for t in range(a[20])]
+        for n in range(N):
+            for ld, lh, lw in itertools.product(range(L[0]), range(L[1]), range(L[2])):
+                d = gyn[n, ld * om[0] + oo[0], lh * om[1] + oo[1], lw * om[2] + oo[2]]
+                for od, oh, ow, tw in taps:
+                    i = (ld * st[0] + od, lh * st[1] + oh, lw * st[2] + ow)
+                    if 0 <= i[0] < Di and 0 <= i[1] < Hi and 0 <= i[2] < Wi:
+                        dw[tw] += np.outer(d, xn[n, i[0], i[1], i[2]])
+    ref = w.grad.numpy().reshape(w.shape[0], w.shape[1], T)
+    ref = np.transpose(ref, (2, 1, 0)) if transposed else np.transpose(ref, (2, 0, 1))      # -> [tap][co][ci]
+    np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
