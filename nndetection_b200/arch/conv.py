@@ -76,8 +76,10 @@ def _grad_target(param, shape, dev):
     """Where a parameter-gradient kernel accumulates (all of them ADD into their destination).  When the parameter already
     owns a dense fp32 `.grad` (the Trainer's flat gradient buffer, zeroed once per step) the kernels add straight into it
     and autograd gets `None` for that input -- no zero-fill, no temporary and no accumulate kernel per parameter
-    (~220 tiny launches per step).  Otherwise a zeroed temporary is returned through autograd as usual."""
-    g = getattr(param, "grad", None) if param is not None else None
+    (~220 tiny launches per step).  Only for parameters whose owner opted in (`param._nnd_direct_grad`, set by
+    training.FlatParameters): a third-party trainer that relies on autograd's AccumulateGrad hooks (torch DDP, as PL
+    would wrap the module) keeps the ordinary path -- a zeroed temporary returned through autograd."""
+    g = getattr(param, "grad", None) if param is not None and getattr(param, "_nnd_direct_grad", False) else None
     if g is not None and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == tuple(shape) and g.device == dev:
         return g, None
     t = torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -140,7 +142,7 @@ class _ConvBlockFn(torch.autograd.Function):
             affine = gamma is not None
             beta_p = layer.norm.bias if affine else None
             if affine:
-                dgamma, dgamma_ret = _grad_target(gamma, (cout,), dev)
+                dgamma, dgamma_ret = _grad_target(layer.norm.weight, (cout,), dev)
                 dbeta, dbeta_ret = _grad_target(beta_p, (cout,), dev)
             ops.norm_backward(dz, y, a, b, mean, rstd, gamma.detach() if affine else None, N, V, cout, layer.norm.cpg,
                               layer.has_act, dy, dgamma, dbeta)
@@ -151,7 +153,7 @@ class _ConvBlockFn(torch.autograd.Function):
         if ctx.has_bias:
             dbias, dbias_ret = _grad_target(conv.bias, (cout,), dev)
             ops.channel_sum(dy, N * V, cout, cout, dbias)
-        dw, dw_ret = _grad_target(weight, tuple(weight.shape), dev)
+        dw, dw_ret = _grad_target(conv.weight, tuple(weight.shape), dev)
         T = plan.T
         if layer.is_first:
             ops.conv_first_wgrad(x, dy, plan.fprop[0], cout, dw)

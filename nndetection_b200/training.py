@@ -43,6 +43,7 @@ class FlatParameters:
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)         # autograd accumulates in place into the flat buffer
+            p._nnd_direct_grad = True                             # ... and the conv / norm kernels add straight into it
             off += k
         self.first_step = True
 

@@ -490,9 +490,18 @@ def test_direct_gradient_accumulation_equals_autograd_accumulation(norm):
         elif mode == "direct":
             for p_ in mine.parameters():
                 p_.grad = torch.zeros_like(p_, dtype=torch.float32)
+                p_._nnd_direct_grad = True               # what training.FlatParameters sets
         mine(x.clone().requires_grad_(True)).backward(gy)
         grads[mode] = {k: p_.grad.detach().clone() for k, p_ in mine.named_parameters()}
+    # without the opt-in flag a pre-existing .grad is NOT written directly (third-party trainers / DDP hooks)
+    for p_ in mine.parameters():
+        p_._nnd_direct_grad = False
+        p_.grad = torch.zeros_like(p_, dtype=torch.float32)
+    mine(x.clone().requires_grad_(True)).backward(gy)
+    grads["plain_with_grad"] = {k: p_.grad.detach().clone() for k, p_ in mine.named_parameters()}
     assert len(grads["autograd"]) == (3 if norm else 2)
+    for k in grads["autograd"]:
+        assert rel_err(grads["plain_with_grad"][k], grads["autograd"][k]) < 1e-5, k
     for k in grads["autograd"]:
         assert rel_err(grads["direct"][k], grads["autograd"][k]) < 1e-5, k
         assert rel_err(grads["direct_twice"][k], 2 * grads["autograd"][k]) < 1e-5, k
