@@ -391,8 +391,33 @@ def cpu_baseline():
     net.postprocess(images, {k: v.detach() for k, v in aux["pred"].items()}, aux["anchors"])
     sum(losses.values()).backward()
     dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "1 train step of 1 patch (fwd+loss+postprocess+bwd), torch CPU fp32"}
+    out = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+           "sample": "1 train step of 1 patch (fwd+loss+postprocess+bwd), torch CPU fp32"}
+    try:
+        out["nms_cpu"] = cpu_nms_rates()
+    except Exception as e:                              # the patches/s baseline above must survive
+        out["nms_cpu"] = {"error": repr(e)}
+    return out
+
+
+def cpu_nms_rates():
+    """The reference's CPU NMS path (nms_cpu, nndet/core/boxes/nms.py:31-53, restated in oracle.box_oracle.nms_greedy) on the
+    same stress boxes as the GPU `nms` block, N = 1 k and 10 k (N = 100 k would need a 40 GB IoU matrix in the reference)."""
+    from oracle import box_oracle as bo
+    res = {}
+    for n in (1_000, 10_000):
+        g = torch.Generator().manual_seed(7)
+        c = torch.rand(n, 3, generator=g) * 160
+        h = torch.rand(n, 3, generator=g) * 20 + 2
+        boxes = torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1], c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], 1)
+        scores = (torch.randperm(n, generator=g).float() + 0.5) / n
+        t0 = time.perf_counter()
+        keep = bo.nms_greedy(boxes, scores, 0.1)
+        dt = time.perf_counter() - t0
+        res[f"n{n}"] = {"ms": 1e3 * dt, "boxes_per_s": n / dt, "kept": int(keep.numel())}
+    res["note"] = ("oracle port: row-wise numpy restatement, 1 thread; the reference's nms_cpu materialises the N x N IoU matrix "
+                   "(SURVEY 8d: 2.09 s at N = 10 k on the survey host)")
+    return res
 
 
 if __name__ == "__main__":
