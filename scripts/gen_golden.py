@@ -157,6 +157,94 @@ def gen_transforms():
     save("transforms", **out)
 
 
+# ------------------------------------------------------------------------------------------ case-level ensembling
+def synth_tile_predictions(seed, case_shape=(64, 96, 80), tile=(32, 48, 40), n_models=2):
+    """Per model / TTA pass: a list of tile batches (2 tiles per batch) with random boxes in tile coordinates."""
+    g = torch.Generator().manual_seed(seed)
+    origins = [(a, b, c) for a in range(0, case_shape[0] - tile[0] + 1, 16) for b in range(0, case_shape[1] - tile[1] + 1, 24)
+               for c in range(0, case_shape[2] - tile[2] + 1, 20)]
+    total = 0
+    models = []
+    for m in range(n_models):
+        batches = []
+        for i in range(0, len(origins), 2):
+            bo_, res = origins[i:i + 2], {"pred_boxes": [], "pred_scores": [], "pred_labels": []}
+            for _ in bo_:
+                n = int(torch.randint(0, 25, (1,), generator=g))
+                lo = torch.rand(n, 3, generator=g) * torch.tensor(tile) * 0.8 - 2.0          # some boxes stick out of the tile
+                sz = torch.rand(n, 3, generator=g) * 10 + 1.0
+                res["pred_boxes"].append(torch.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0], lo[:, 1] + sz[:, 1], lo[:, 2],
+                                                      lo[:, 2] + sz[:, 2]], dim=1))
+                res["pred_scores"].append(torch.empty(n))                                    # filled below (unique scores)
+                res["pred_labels"].append(torch.randint(0, 2, (n,), generator=g))
+                total += n
+            batch = {"tile_origin": [torch.tensor([o[ax] for o in bo_]) for ax in range(3)], "data": torch.zeros(len(bo_), 1, *tile)}
+            batches.append((res, batch))
+        models.append(batches)
+    sc = (torch.randperm(total, generator=g).float() + 0.5) / total
+    k = 0
+    for batches in models:
+        for res, _ in batches:
+            for j, t in enumerate(res["pred_scores"]):
+                res["pred_scores"][j] = sc[k:k + t.numel()]; k += t.numel()
+    return models, case_shape
+
+
+def gen_ensembler():
+    """BoxEnsemblerSelective (nndet/inference/ensembler/detection.py:901-1130) executed from its files; the package __init__
+    modules that pull ITK / predictor code are replaced by path-only stand-ins, `nndet.io.load` / `nndet.inference.restore` by stubs."""
+    import importlib, types
+    root = ref_import.REF_ROOT
+    for name, sub in (("nndet.inference", "nndet/inference"), ("nndet.inference.ensembler", "nndet/inference/ensembler")):
+        if name not in sys.modules or not hasattr(sys.modules[name], "__path__"):
+            pkg = types.ModuleType(name); pkg.__path__ = [os.path.join(root, sub)]; sys.modules[name] = pkg
+    io = sys.modules.setdefault("nndet.io", types.ModuleType("nndet.io"))
+    load = types.ModuleType("nndet.io.load"); load.save_pickle = lambda *a, **k: None
+    sys.modules["nndet.io.load"] = load; io.load = load
+    rest = types.ModuleType("nndet.inference.restore"); rest.restore_detection = lambda boxes, **k: boxes
+    sys.modules["nndet.inference.restore"] = rest
+    det = importlib.import_module("nndet.inference.ensembler.detection")
+    from nndetection_b200.inference import ensembler as mine
+
+    def o_weighted_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+        keep = bo.batched_nms(boxes, scores * weights, labels, iou_thresh, cuda_semantics=False)
+        return boxes[keep], scores[keep], labels[keep], torch.ones_like(weights)[keep]
+
+    def o_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+        keep = bo.batched_nms(boxes, scores, labels, iou_thresh, cuda_semantics=False)
+        return boxes[keep], scores[keep], labels[keep], weights[keep]
+
+    def o_wbc_ensemble(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh, *a, **k):
+        return bo.batched_wbc(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh)
+
+    out = {}
+    for ci, (seed, overrides, mine_over) in enumerate([
+            (1, {}, {"model_nms_fn": o_weighted_nms_model, "ensemble_nms_fn": o_wbc_ensemble}),
+            (2, {"model_iou": 0.3, "ensemble_iou": 0.2, "model_score_thresh": 0.1, "remove_small_boxes": 2.0,
+                 "model_nms_fn": det.batched_nms_model},
+             {"model_iou": 0.3, "ensemble_iou": 0.2, "model_score_thresh": 0.1, "remove_small_boxes": 2.0,
+              "model_nms_fn": o_nms_model, "ensemble_nms_fn": o_wbc_ensemble})]):
+        models, shape = synth_tile_predictions(seed)
+        props = {"shape": shape, "original_size_of_raw_data": shape, "itk_origin": (0, 0, 0), "itk_spacing": (1, 1, 1),
+                 "itk_direction": (1, 0, 0, 0, 1, 0, 0, 0, 1)}
+        rp = det.BoxEnsemblerSelective.get_default_parameters(); rp.update(overrides)
+        ref = det.BoxEnsemblerSelective(properties=dict(props), parameters=rp)
+        mp = mine.BoxEnsemblerSelective.get_default_parameters(); mp.update(mine_over)
+        my = mine.BoxEnsemblerSelective(properties=dict(props), parameters=mp)
+        for mi, batches in enumerate(models):
+            ref.add_model(name=f"model0_t{mi}", model_weight=1.0 if mi == 0 else 0.7)
+            my.add_model(name=f"model0_t{mi}", model_weight=1.0 if mi == 0 else 0.7)
+            for res, batch in batches:
+                ref.process_batch(result={k: [t.clone() for t in v] for k, v in res.items()}, batch=batch)
+                my.process_batch(result={k: [t.clone() for t in v] for k, v in res.items()}, batch=batch)
+        r, m = ref.get_case_result(restore=False), my.get_case_result(restore=False)
+        for k in ("pred_boxes", "pred_scores", "pred_labels"):
+            assert r[k].shape == m[k].shape and torch.equal(r[k].float(), m[k].float()), (ci, k)
+        assert r["pred_boxes"].shape[0] > 10
+        out[f"c{ci}_boxes"] = r["pred_boxes"]; out[f"c{ci}_scores"] = r["pred_scores"]; out[f"c{ci}_labels"] = r["pred_labels"]
+    save("ensembler", **out)
+
+
 # ------------------------------------------------------------------------------------------ box metrics
 def gen_pairwise():
     g = torch.Generator().manual_seed(11)
@@ -424,7 +512,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

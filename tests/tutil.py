@@ -76,3 +76,35 @@ def synth_instances(B, shape, seed, nmax=6):
             mp[str(i)] = int(rs.randint(0, 3))
         maps.append(mp)
     return t, maps
+
+
+def synth_tile_predictions(seed, case_shape=(64, 96, 80), tile=(32, 48, 40), n_models=2):
+    """Same generator as scripts/gen_golden.py:synth_tile_predictions."""
+    g = torch.Generator().manual_seed(seed)
+    origins = [(a, b, c) for a in range(0, case_shape[0] - tile[0] + 1, 16) for b in range(0, case_shape[1] - tile[1] + 1, 24)
+               for c in range(0, case_shape[2] - tile[2] + 1, 20)]
+    total = 0
+    models = []
+    for m in range(n_models):
+        batches = []
+        for i in range(0, len(origins), 2):
+            bo_, res = origins[i:i + 2], {"pred_boxes": [], "pred_scores": [], "pred_labels": []}
+            for _ in bo_:
+                n = int(torch.randint(0, 25, (1,), generator=g))
+                lo = torch.rand(n, 3, generator=g) * torch.tensor(tile) * 0.8 - 2.0
+                sz = torch.rand(n, 3, generator=g) * 10 + 1.0
+                res["pred_boxes"].append(torch.stack([lo[:, 0], lo[:, 1], lo[:, 0] + sz[:, 0], lo[:, 1] + sz[:, 1], lo[:, 2],
+                                                      lo[:, 2] + sz[:, 2]], dim=1))
+                res["pred_scores"].append(torch.empty(n))
+                res["pred_labels"].append(torch.randint(0, 2, (n,), generator=g))
+                total += n
+            batch = {"tile_origin": [torch.tensor([o[ax] for o in bo_]) for ax in range(3)], "data": torch.zeros(len(bo_), 1, *tile)}
+            batches.append((res, batch))
+        models.append(batches)
+    sc = (torch.randperm(total, generator=g).float() + 0.5) / total
+    k = 0
+    for batches in models:
+        for res, _ in batches:
+            for j, t in enumerate(res["pred_scores"]):
+                res["pred_scores"][j] = sc[k:k + t.numel()]; k += t.numel()
+    return models, case_shape
