@@ -245,6 +245,132 @@ def gen_ensembler():
     save("ensembler", **out)
 
 
+# ------------------------------------------------------------------------------------------ sliding-window predictor
+class FakeDetector:
+    """Deterministic stand-in for a model: detections are a function of the tile content only (so mirrored tiles give mirrored
+    detections only if the pipeline un-mirrors them correctly)."""
+
+    def eval(self):
+        return self
+
+    def inference_step(self, images):
+        out = {"pred_boxes": [], "pred_scores": [], "pred_labels": [], "pred_seg": torch.zeros(images.shape[0], 2, *images.shape[2:])}
+        D, H, W = images.shape[2:]
+        for img in images[:, 0]:
+            flat = img.reshape(-1)
+            idx = torch.argsort(flat, descending=True, stable=True)[:6]
+            z = torch.div(idx, H * W, rounding_mode="floor"); y = torch.div(idx % (H * W), W, rounding_mode="floor"); x = idx % W
+            c = torch.stack([z, y, x], 1).float()
+            half = 2.0 + 6.0 * flat[idx][:, None] * torch.tensor([1.0, 0.7, 0.5])
+            out["pred_boxes"].append(torch.stack([c[:, 0] - half[:, 0], c[:, 1] - half[:, 1], c[:, 0] + half[:, 0], c[:, 1] + half[:, 1],
+                                                  c[:, 2] - half[:, 2], c[:, 2] + half[:, 2]], 1))
+            # unique scores: the same voxel is seen by overlapping tiles and by every mirrored copy -- a content- and
+            # orientation-dependent offset keeps all scores distinct (torch.sort leaves the order of ties unspecified)
+            ramp = torch.arange(flat.numel(), dtype=torch.float32)
+            salt = float((flat * ((ramp * 0.6180339887) % 1.0)).sum() % 1.0)
+            out["pred_scores"].append((flat[idx] * 0.9 + 0.1 * salt).clone())
+            out["pred_labels"].append(((z + y + x) % 2).long())
+        return out
+
+
+GRID_CASES = [(32, 40, 16), (32, 56, 16), (32, 32, 16), (48, 40, 24), (16, 100, 4), (20, 61, 10), (8, 8, 0)]
+
+
+def gen_predictor():
+    """Tile grid (nndet/io/patching.py), Mirror (nndet/io/transforms/spatial.py) and BoxEnsemblerSelective executed from their files;
+    the predictor loop of nndet/inference/predictor.py:192-306 is restated around them (its module needs a DataLoader / ITK stack)."""
+    import importlib, importlib.util, types
+    root = ref_import.REF_ROOT
+    sk = types.ModuleType("skimage"); skm = types.ModuleType("skimage.measure"); skm.regionprops = None
+    sys.modules.setdefault("skimage", sk); sys.modules.setdefault("skimage.measure", skm)
+
+    class _AT(torch.nn.Module):
+        def __init__(self, grad=False, **kw):
+            super().__init__(); self.grad = grad
+
+        def __call__(self, **data):
+            return self.forward(**data)
+    base = types.ModuleType("nndet.io.transforms.base"); base.AbstractTransform = _AT
+    for name in ("nndet.io", "nndet.io.transforms"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["nndet.io.transforms.base"] = base
+
+    def load(modname, rel):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    rpatch = load("ref_patching", "nndet/io/patching.py")
+    rspat = load("ref_spatial", "nndet/io/transforms/spatial.py")
+    for name, sub in (("nndet.inference", "nndet/inference"), ("nndet.inference.ensembler", "nndet/inference/ensembler")):
+        if name not in sys.modules or not hasattr(sys.modules[name], "__path__"):
+            pkg = types.ModuleType(name); pkg.__path__ = [os.path.join(root, sub)]; sys.modules[name] = pkg
+    ld = types.ModuleType("nndet.io.load"); ld.save_pickle = lambda *a, **k: None; sys.modules["nndet.io.load"] = ld
+    rest = types.ModuleType("nndet.inference.restore"); rest.restore_detection = lambda boxes, **k: boxes
+    sys.modules["nndet.inference.restore"] = rest
+    det = importlib.import_module("nndet.inference.ensembler.detection")
+    from nndetection_b200.inference import predictor as mp, ensembler as me
+
+    out = {}
+    # ---- grids: both modes, with / without centre-border crops
+    for gi, (ps, dl, ov) in enumerate(GRID_CASES):
+        for mode in ("fixed", "symmetric"):
+            for cb in (False, True):
+                r = rpatch.create_grid((ps, ps), (dl, dl + 7), (ov, ov), mode=mode, center_boarder=cb)
+                m = mp.create_grid((ps, ps), (dl, dl + 7), (ov, ov), mode=mode, center_boarder=cb)
+                assert [[(s.start, s.stop) for s in c] for c in r] == [[(s.start, s.stop) for s in c] for c in m]
+                out[f"grid{gi}_{mode}_{int(cb)}"] = np.asarray([[(s.start, s.stop) for s in c] for c in r], dtype=np.int64)
+    # ---- box mirroring
+    g = torch.Generator().manual_seed(3)
+    bx = rand_boxes(50, g, extent=30.0, lo=1.0, hi=6.0)
+    for dims in [(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)]:
+        r = rspat.Mirror(keys=["pred_seg"], box_keys=["pred_boxes"], dims=dims)(pred_seg=torch.zeros(1, 2, 32, 40, 24), pred_boxes=[bx])
+        assert torch.equal(r["pred_boxes"][0], mp.mirror_boxes(bx, dims, (32, 40, 24)))
+    # ---- whole loop: case -> tiles -> 8 mirror TTAs -> ensembler
+    g = torch.Generator().manual_seed(17)
+    case = {"data": torch.rand(1, 40, 56, 48, generator=g).numpy()}
+    crop_size, bs = (32, 32, 32), 4
+    props = {"transpose_backward": None, "original_spacing": None, "spacing_after_resampling": None, "crop_bbox": None,
+             "original_size_of_raw_data": (40, 56, 48), "itk_origin": (0, 0, 0), "itk_spacing": (1, 1, 1), "itk_direction": (1, 0, 0, 0, 1, 0, 0, 0, 1)}
+    model = FakeDetector()
+    ens = det.BoxEnsemblerSelective.from_case(case, props, parameters={})
+    crops = rpatch.create_grid(cshape=crop_size, dshape=case["data"].shape[1:], overlap=[int(c * 0.5) for c in crop_size], mode="symmetric")
+    tiles = []
+    for crop in crops:                                                    # predictor.py:214-235
+        tile = {"data": rpatch.save_get_crop(case["data"], crop, mode="shift")[0]}
+        _, tile["tile_origin"], tile["crop"] = rpatch.save_get_crop(case["data"], crop, mode="shift")
+        tiles.append(tile)
+    for t, dims in enumerate(mp.get_tta_dims(8)):                         # predictor.py:258-273, inference/transforms.py:25-72
+        ens.add_model(name=f"model0_t{t}", model_weight=1.0)
+        for i in range(0, len(tiles), bs):
+            chunk = tiles[i:i + bs]
+            batch = {"data": torch.stack([torch.from_numpy(np.ascontiguousarray(c["data"])) for c in chunk]),
+                     "tile_origin": [torch.tensor([c["tile_origin"][ax] for c in chunk]) for ax in range(3)]}
+            tr = rspat.Mirror(keys=["data"], dims=dims)(**batch) if dims else batch
+            res = model.inference_step(tr["data"])
+            if dims:
+                res = rspat.Mirror(keys=["pred_seg"], box_keys=["pred_boxes"], dims=dims)(**res)
+            ens.process_batch(result=res, batch=batch)
+    ref = ens.get_case_result(restore=False)
+
+    def o_weighted_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+        keep = bo.batched_nms(boxes, scores * weights, labels, iou_thresh, cuda_semantics=False)
+        return boxes[keep], scores[keep], labels[keep], torch.ones_like(weights)[keep]
+
+    def o_wbc_ensemble(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh, *a, **k):
+        return bo.batched_wbc(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh)
+    pred = mp.SlidingWindowPredictor(
+        ensembler_fn=lambda c, properties=None: me.BoxEnsemblerSelective.from_case(
+            c, properties, parameters={"model_nms_fn": o_weighted_nms_model, "ensemble_nms_fn": o_wbc_ensemble}),
+        models=[model], crop_size=crop_size, overlap=0.5, num_tta_transforms=8, batch_size=bs, device="cpu")
+    mine_res = pred.predict_case({"data": torch.from_numpy(case["data"])}, properties=props)["boxes"]
+    for k in ("pred_boxes", "pred_scores", "pred_labels"):
+        assert ref[k].shape == mine_res[k].shape and torch.equal(ref[k].float(), mine_res[k].float()), k
+    print(f"  predictor case: {len(tiles)} tiles, {ref['pred_boxes'].shape[0]} final boxes")
+    assert ref["pred_boxes"].shape[0] >= 5 and len(tiles) >= 8
+    out["case_boxes"] = ref["pred_boxes"]; out["case_scores"] = ref["pred_scores"]; out["case_labels"] = ref["pred_labels"]
+    out["tile_origins"] = np.asarray([t["tile_origin"] for t in tiles], dtype=np.int64)
+    save("predictor", **out)
+
+
 # ------------------------------------------------------------------------------------------ box metrics
 def gen_pairwise():
     g = torch.Generator().manual_seed(11)
@@ -512,7 +638,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

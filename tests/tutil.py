@@ -108,3 +108,30 @@ def synth_tile_predictions(seed, case_shape=(64, 96, 80), tile=(32, 48, 40), n_m
             for j, t in enumerate(res["pred_scores"]):
                 res["pred_scores"][j] = sc[k:k + t.numel()]; k += t.numel()
     return models, case_shape
+
+
+GRID_CASES = [(32, 40, 16), (32, 56, 16), (32, 32, 16), (48, 40, 24), (16, 100, 4), (20, 61, 10), (8, 8, 0)]
+
+
+class FakeDetector:
+    """Same deterministic stand-in model as scripts/gen_golden.py:FakeDetector (detections = function of the tile content)."""
+
+    def eval(self):
+        return self
+
+    def inference_step(self, images):
+        out = {"pred_boxes": [], "pred_scores": [], "pred_labels": [], "pred_seg": torch.zeros(images.shape[0], 2, *images.shape[2:])}
+        D, H, W = images.shape[2:]
+        for img in images[:, 0]:
+            flat = img.reshape(-1)
+            idx = torch.argsort(flat, descending=True, stable=True)[:6]
+            z = torch.div(idx, H * W, rounding_mode="floor"); y = torch.div(idx % (H * W), W, rounding_mode="floor"); x = idx % W
+            c = torch.stack([z, y, x], 1).float()
+            half = 2.0 + 6.0 * flat[idx][:, None] * torch.tensor([1.0, 0.7, 0.5])
+            out["pred_boxes"].append(torch.stack([c[:, 0] - half[:, 0], c[:, 1] - half[:, 1], c[:, 0] + half[:, 0], c[:, 1] + half[:, 1],
+                                                  c[:, 2] - half[:, 2], c[:, 2] + half[:, 2]], 1))
+            ramp = torch.arange(flat.numel(), dtype=torch.float32)
+            salt = float((flat * ((ramp * 0.6180339887) % 1.0)).sum() % 1.0)
+            out["pred_scores"].append((flat[idx] * 0.9 + 0.1 * salt).clone())
+            out["pred_labels"].append(((z + y + x) % 2).long())
+        return out
