@@ -225,6 +225,48 @@ class BoxEnsemblerSelective:
         return self.parameters["ensemble_nms_fn"](boxes, probs, labels, weights=weights, iou_thresh=self.parameters["ensemble_iou"],
                                                   n_exp_preds=n_exp_preds, score_thresh=self.parameters["ensemble_score_thresh"])
 
+    # ---- on-disk state (ensembler/base.py:176-222, detection.py:276-318,1132-1163): `<case>_boxes.pt`, same keys
+    def save_state(self, target_dir, name: str, **kwargs):
+        """Per model only the `model_topk` best predictions are kept (detection.py:1150-1161), tensors are stored on the CPU (the
+        reference's note at :288-290), keys as written by `BaseEnsembler.save_state` + `BoxEnsembler.save_state`."""
+        from pathlib import Path
+        for model, r in self.model_results.items():
+            like = r["boxes"][0] if r["boxes"] else None
+            boxes, probs = _cat(list(r["boxes"]), like, 6), _cat(list(r["scores"]), like)
+            labels, weights = _cat(list(r["labels"]), like), _cat(list(r["weights"]), like)
+            if len(probs) > self.parameters["model_topk"]:
+                idx = torch.argsort(probs, descending=True, stable=True)[:self.parameters["model_topk"]]
+                boxes, probs, labels, weights = boxes[idx], probs[idx], labels[idx], weights[idx]
+            r["boxes"], r["scores"], r["labels"], r["weights"] = [boxes.cpu()], [probs.cpu()], [labels.cpu()], [weights.cpu()]
+        state = dict(kwargs)
+        state.update(properties=self.properties, parameters=self.parameters, model_current=self.model_current,
+                     model_results={k: dict(v) for k, v in self.model_results.items()}, model_weights=self.model_weights,
+                     case_result=self.case_result, score_key=self.score_key, label_key=self.label_key, box_key=self.box_key,
+                     data_key=self.data_key, overlap_map=None)
+        with open(Path(target_dir) / f"{name}_{self.ID}.pt", "wb") as f:
+            torch.save(state, f)
+
+    @classmethod
+    def from_checkpoint(cls, base_dir, case_id: str, **kwargs):
+        """detection.py:304-318."""
+        from pathlib import Path
+        ckp = torch.load(str(Path(base_dir) / f"{case_id}_{cls.ID}.pt"), weights_only=False)
+        t = cls(properties=ckp["properties"], parameters=ckp["parameters"], box_key=ckp["box_key"], score_key=ckp["score_key"],
+                label_key=ckp["label_key"], data_key=ckp["data_key"], **kwargs)
+        for key, item in ckp.items():
+            if key == "model_results":
+                item = {k: defaultdict(list, {kk: (list(vv) if isinstance(vv, (list, tuple)) else [vv]) for kk, vv in v.items()})
+                        for k, v in item.items()}
+            if key != "overlap_map":
+                setattr(t, key, item)
+        return t
+
+    @classmethod
+    def get_case_ids(cls, base_dir) -> List[str]:
+        """ensembler/base.py:224-227."""
+        from pathlib import Path
+        return [c.stem.rsplit(f"_{cls.ID}", 1)[0] for c in Path(base_dir).glob(f"*_{cls.ID}.pt")]
+
     @torch.no_grad()
     def get_case_result(self, restore: bool = False, names: Optional[Sequence[Hashable]] = None) -> Dict[str, Any]:
         """detection.py:422-474."""

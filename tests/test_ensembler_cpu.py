@@ -65,3 +65,27 @@ def test_defaults_and_protocol():
     # in-tile weight: 1 on the plateau, 0.5 in the corner (detection.py:1036-1060)
     w = E.BoxEnsemblerSelective._get_box_in_tile_weight(torch.tensor([[16., 24, 20], [0., 0, 0]]), (32, 48, 40))
     assert torch.allclose(w, torch.tensor([1.0, 0.5]))
+
+
+def test_state_round_trip(tmp_path):
+    """`<case>_boxes.pt` (ensembler/base.py:176-222, detection.py:276-318): saved state reloads into an ensembler that gives the
+    same case result; only `model_topk` predictions per model are stored."""
+    from nndetection_b200.inference.ensembler import BoxEnsemblerSelective
+    seed, over = CASES[0]
+    models, shape = util.synth_tile_predictions(seed)
+    params = BoxEnsemblerSelective.get_default_parameters()
+    params.update(over)
+    params["model_topk"] = 150
+    ens = BoxEnsemblerSelective.from_case({"data": torch.zeros(1, *shape)}, properties={}, parameters=params)
+    for mi, batches in enumerate(models):
+        ens.add_model(name=f"model0_t{mi}", model_weight=1.0 if mi == 0 else 0.7)
+        for res, batch in batches:
+            ens.process_batch(result=res, batch=batch)
+    ref = ens.get_case_result()
+    ens.save_state(tmp_path, "case_007")
+    assert BoxEnsemblerSelective.get_case_ids(tmp_path) == ["case_007"]
+    ens2 = BoxEnsemblerSelective.from_checkpoint(tmp_path, "case_007")
+    assert all(v["boxes"][0].shape[0] <= 150 for v in ens2.model_results.values())
+    out = ens2.get_case_result()
+    for k in ("pred_boxes", "pred_scores", "pred_labels"):
+        assert torch.equal(out[k], ref[k])
