@@ -52,11 +52,20 @@ class FlatParameters:
 
 
 def poly_lr(step: int, initial_lr: float, warm_iterations: int, warm_lr: float, poly_gamma: float, num_iterations: int) -> float:
-    """LinearWarmupPolyLR (nndet/training/learning_rate.py): linear warm-up from warm_lr, then polynomial decay."""
+    """Learning rate of optimizer step `step` (0-based) under the reference's `LinearWarmupPolyLR` stepped once per batch
+    (nndet/training/learning_rate.py:126-183, configured at nndet/ptmodule/retinaunet/base.py:329-336).  The reference evaluates its
+    formulas with torch's `_step_count`, which is already 1 when the first batch runs, so step s uses iteration s + 1:
+        s <  warm_iterations : warm_lr + (initial_lr - warm_lr) * (s + 1) / warm_iterations            (linear_warm_up, :27-49)
+        s >= warm_iterations : initial_lr * (1 - it / poly_iterations) ** gamma, it = s + 1 - warm_iterations, clamped to
+                               poly_iterations - 1 once the schedule is over                           (poly_lr, :52-78)
+    Pinned against the executed reference scheduler: tests/golden/lr.npz."""
     if step < warm_iterations:
-        return warm_lr + (initial_lr - warm_lr) * step / max(1, warm_iterations)
-    t = (step - warm_iterations) / max(1, num_iterations - warm_iterations)
-    return initial_lr * (1 - min(t, 1.0)) ** poly_gamma
+        return warm_lr + (initial_lr - warm_lr) * (float(step + 1) / float(warm_iterations))
+    poly_iterations = num_iterations - warm_iterations
+    it = step + 1 - warm_iterations
+    if it >= poly_iterations:
+        it = poly_iterations - 1
+    return initial_lr * (1 - it / float(poly_iterations)) ** poly_gamma
 
 
 class Trainer:

@@ -371,6 +371,28 @@ def gen_predictor():
     save("predictor", **out)
 
 
+# ------------------------------------------------------------------------------------------ learning-rate schedule
+def gen_lr():
+    """LinearWarmupPolyLR (nndet/training/learning_rate.py:126-183) executed: the lr the optimizer holds at every step."""
+    import importlib.util
+    from nndetection_b200.training import poly_lr
+    spec = importlib.util.spec_from_file_location("ref_lr", os.path.join(ref_import.REF_ROOT, "nndet/training/learning_rate.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    cfgs = [(0.01, 40, 1e-6, 0.9, 200), (0.01, 4000, 1e-6, 0.9, 6000)]
+    out = {"cfgs": np.asarray(cfgs, dtype=np.float64)}
+    for i, (lr0, warm, wlr, gamma, n) in enumerate(cfgs):
+        p_ = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p_], lr=lr0)
+        sch = m.LinearWarmupPolyLR(opt, warm_iterations=warm, warm_lr=wlr, poly_gamma=gamma, num_iterations=n)
+        lrs = []
+        for step in range(n - 1):
+            lrs.append(opt.param_groups[0]["lr"])
+            assert lrs[-1] == poly_lr(step, lr0, warm, wlr, gamma, n), (i, step, lrs[-1], poly_lr(step, lr0, warm, wlr, gamma, n))
+            opt.step(); sch.step()
+        out[f"lrs{i}"] = np.asarray(lrs, dtype=np.float64)
+    save("lr", **out)
+
+
 # ------------------------------------------------------------------------------------------ box metrics
 def gen_pairwise():
     g = torch.Generator().manual_seed(11)
@@ -638,7 +660,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "lr", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -67,16 +67,22 @@ def test_two_rank_gradient_mean_matches_single_process():
     ((out - y) ** 2).mean().backward()
     flat_p = torch.cat([p.data.reshape(-1) for p in params])
     flat_g = torch.cat([p.grad.reshape(-1) for p in params])
-    ref, _ = _sgd_reference(flat_p, flat_g, torch.zeros_like(flat_p), 0.01, 0.9, 3e-5, True, True)
+    from nndetection_b200.training import poly_lr
+    lr = poly_lr(0, 0.01, 0, 1e-6, 0.9, 100)
+    ref, _ = _sgd_reference(flat_p, flat_g, torch.zeros_like(flat_p), lr, 0.9, 3e-5, True, True)
     nd = flat_p.numel() - 8
-    ref[nd:] = _sgd_reference(flat_p[nd:], flat_g[nd:], torch.zeros(8), 0.01, 0.9, 0.0, True, True)[0]
+    ref[nd:] = _sgd_reference(flat_p[nd:], flat_g[nd:], torch.zeros(8), lr, 0.9, 0.0, True, True)[0]
     assert torch.allclose(ret[0], ref, rtol=1e-5, atol=1e-7)
 
 
-def test_lr_schedule_matches_reference_formula():
+def test_lr_schedule_matches_reference_scheduler():
+    """nndetection_b200.training.poly_lr vs the EXECUTED reference `LinearWarmupPolyLR` (one scheduler step per optimizer step),
+    tests/golden/lr.npz from scripts/gen_golden.py lr: identical doubles for every step of two schedules."""
+    import numpy as np
+    import tutil as util
     from nndetection_b200.training import poly_lr
-    assert abs(poly_lr(0, 0.01, 4000, 1e-6, 0.9, 125000) - 1e-6) < 1e-12
-    assert abs(poly_lr(4000, 0.01, 4000, 1e-6, 0.9, 125000) - 0.01) < 1e-12
-    assert poly_lr(125000, 0.01, 4000, 1e-6, 0.9, 125000) == 0.0
-    mid = poly_lr(64500, 0.01, 4000, 1e-6, 0.9, 125000)
-    assert abs(mid - 0.01 * 0.5 ** 0.9) < 1e-9
+    g = util.golden("lr")
+    for i, (lr0, warm, wlr, gamma, n) in enumerate(g["cfgs"].tolist()):
+        ref = g[f"lrs{i}"]
+        mine = np.asarray([poly_lr(s, lr0, int(warm), wlr, gamma, int(n)) for s in range(len(ref))])
+        assert np.array_equal(mine, ref), i
