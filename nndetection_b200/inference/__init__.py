@@ -4,3 +4,5 @@ from .wbc import batched_wbc, wbc  # noqa: F401
 from .ensembler import (BoxEnsemblerSelective, batched_nms_ensemble, batched_nms_model, batched_wbc_ensemble,  # noqa: F401
                         batched_weighted_nms_model, wbc_nms_no_label_ensemble)
 from .predictor import SlidingWindowPredictor, create_grid, get_tta_dims, mirror_boxes  # noqa: F401
+from .helper import (get_loader_fn, get_predictor, load_all_models, load_final_model, predict_dir,  # noqa: F401
+                     save_checkpoint)

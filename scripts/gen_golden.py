@@ -371,6 +371,101 @@ def gen_predictor():
     save("predictor", **out)
 
 
+# ------------------------------------------------------------------------------------------ predict_dir + on-disk formats
+HELPER_PROPS = {"original_size_of_raw_data": (40, 56, 48), "itk_origin": (0.0, 0.0, 0.0), "itk_spacing": (1.0, 1.0, 1.0),
+                "itk_direction": (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)}
+
+
+def gen_helper():
+    """`get_case_id_from_path` (nndet/io/paths.py), `save_pickle` / `load_pickle` (nndet/io/load.py) and `to_numpy` (nndet/utils/tensor.py)
+    executed from their files: the `<case>_boxes.pkl` the reference's `predict_dir` (nndet/inference/helper.py:109-110) writes for the
+    case result of tests/golden/predictor.npz (itself produced by the executed ensembler), against the file this package's `predict_dir`
+    writes for the same case -- byte for byte here, content (key order, dtypes, values) in the fixture."""
+    import importlib.util, tempfile, types, pickle
+    root = ref_import.REF_ROOT
+
+    def load(modname, rel):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    rpaths = load("ref_paths", "nndet/io/paths.py")
+    for name in ("nndet.io",):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    saved = sys.modules.get("nndet.io.paths")
+    sys.modules["nndet.io.paths"] = rpaths
+    rload = load("ref_load", "nndet/io/load.py")
+    if saved is not None:
+        sys.modules["nndet.io.paths"] = saved
+    rtensor = load("ref_tensor", "nndet/utils/tensor.py")
+    from nndetection_b200.inference import helper as mh
+
+    names = ["/data/Task000/imagesTr/case_001_0000.nii.gz", "/x/y/LUNA_17.npz", "/p/q.r/abc.def.npy", "/a/b_0000.nii.gz"]
+    for n in names:
+        for rm in (True, False):
+            assert rpaths.get_case_id_from_path(n, remove_modality=rm) == mh.get_case_id_from_path(n, remove_modality=rm), (n, rm)
+
+    g = np.load(os.path.join(OUT, "predictor.npz"))
+    ref_result = {"boxes": {"pred_boxes": torch.from_numpy(g["case_boxes"]), "pred_scores": torch.from_numpy(g["case_scores"]),
+                            "pred_labels": torch.from_numpy(g["case_labels"]), "restore": False, **HELPER_PROPS}}
+
+    def o_weighted_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+        keep = bo.batched_nms(boxes, scores * weights, labels, iou_thresh, cuda_semantics=False)
+        return boxes[keep], scores[keep], labels[keep], torch.ones_like(weights)[keep]
+
+    def o_wbc_ensemble(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh, *a, **k):
+        return bo.batched_wbc(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh)
+
+    with tempfile.TemporaryDirectory() as td:
+        src, dst_ref, dst_mine = os.path.join(td, "src"), os.path.join(td, "ref"), os.path.join(td, "mine")
+        for d in (src, dst_ref, dst_mine):
+            os.makedirs(d)
+        gen = torch.Generator().manual_seed(17)
+        np.savez(os.path.join(src, "case_a.npz"), data=torch.rand(1, 40, 56, 48, generator=gen).numpy())
+        rload.save_pickle(dict(HELPER_PROPS), os.path.join(src, "case_a"))                 # suffix added by the reference helper
+        assert os.path.isfile(os.path.join(src, "case_a.pkl"))
+        assert mh.load_pickle(os.path.join(src, "case_a")) == rload.load_pickle(os.path.join(src, "case_a")) == HELPER_PROPS
+        for key, item in rtensor.to_numpy(ref_result).items():                             # nndet/inference/helper.py:109-110
+            rload.save_pickle(item, os.path.join(dst_ref, f"case_a_{key}.pkl"))
+        plan = {"patch_size": (32, 32, 32), "batch_size": 4, "network_dim": 3, "transpose_backward": [0, 1, 2],
+                "inference_plan": {"model_nms_fn": o_weighted_nms_model, "ensemble_nms_fn": o_wbc_ensemble}}
+        mh.predict_dir(src, dst_mine, cfg={}, plan=plan, source_models=td, model_fn=lambda *a: [{"model": FakeDetector(), "rank": 0}],
+                       num_models=1, device="cpu")
+        a = open(os.path.join(dst_ref, "case_a_boxes.pkl"), "rb").read()
+        b = open(os.path.join(dst_mine, "case_a_boxes.pkl"), "rb").read()
+        assert a == b, "case_a_boxes.pkl differs from the file the reference helpers write"
+        res = pickle.loads(a)
+    # ---- checkpoints: the REAL reference network inside a stand-in LightningModule (attribute `model`, nndet/ptmodule/base_module.py:55-59)
+    #      written the way Lightning does ({"state_dict": module.state_dict()}) and read the way loading.py:96-97 does
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    arch, anc, patch, bs = mo.make_plan("tiny")
+
+    class LM(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__(); self.model = net
+    torch.manual_seed(1)
+    lm = LM(build_reference_model(dict(arch), dict(anc)))
+    with tempfile.TemporaryDirectory() as td:
+        torch.save({"state_dict": lm.state_dict(), "epoch": 3, "global_step": 7500}, os.path.join(td, "model_last.ckpt"))
+        mine = mh.load_final_model(td, {"model_cfg": None}, {"architecture": arch, "anchors": anc}, num_models=1, identifier="last", device=None)[0]["model"]
+        for k, v in lm.model.state_dict().items():
+            assert torch.equal(v, mine.state_dict()[k]), k
+        torch.manual_seed(2)
+        other = RetinaUNetV001.from_config_plan(None, arch, anc)
+        mh.save_checkpoint(other, os.path.join(td, "model_best.ckpt"), epoch=1)
+        state_dict = torch.load(os.path.join(td, "model_best.ckpt"), map_location="cpu")["state_dict"]      # loading.py:96
+        t = lm.load_state_dict(state_dict)                                                                    # loading.py:97 (strict)
+        assert not t.missing_keys and not t.unexpected_keys
+        for k, v in other.state_dict().items():
+            assert torch.equal(v.float(), lm.model.state_dict()[k]), k
+        assert len(mh.load_all_models(td, {"model_cfg": None}, {"architecture": arch, "anchors": anc}, device=None)) == 2
+    print("  checkpoints: reference-layout .ckpt loads into this package's network and back (strict, all tensors equal)")
+    out = {"keys": np.asarray(list(res.keys())), "dtypes": np.asarray([str(getattr(v, "dtype", type(v).__name__)) for v in res.values()])}
+    for k in ("pred_boxes", "pred_scores", "pred_labels"):
+        out[k] = res[k]
+    print(f"  case_a_boxes.pkl: {len(a)} bytes identical, keys {list(res.keys())}")
+    save("helper", **out)
+
+
 # ------------------------------------------------------------------------------------------ learning-rate schedule
 def gen_lr():
     """LinearWarmupPolyLR (nndet/training/learning_rate.py:126-183) executed: the lr the optimizer holds at every step."""
@@ -660,7 +755,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "lr", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "helper", "lr", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()
