@@ -297,6 +297,13 @@ def main():
             out["nms"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
+                # free this arm's buffers first: the stock path keeps fp32 + fp16 activations of every layer (tens of GB)
+                del trainer, net, resident
+                torch.cuda.empty_cache()
+                out["gpu_baseline"] = stock_gpu_baseline(dev, args.config)
+            except Exception as e:                       # a comparator, never allowed to cost the result line
+                out["gpu_baseline"] = {"value": None, "unit": UNIT, "kind": "stock PyTorch/cuDNN modules", "sample": f"failed: {e!r}"}
+            try:
                 out["cpu_baseline"] = cpu_baseline()
             except Exception as e:                       # never lose the GPU line to a host-side problem
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
@@ -375,6 +382,61 @@ def nms_rates(dev):
         res[f"n{n}"] = {"ms": ms, "boxes_per_s": n / (ms / 1e3), "kept": k, "algorithmic_GB_per_s": byt / (ms / 1e3) / 1e9,
                         "pair_tests_per_s": 0.5 * n * (n - 1) / (ms / 1e3)}
     return res
+
+
+def stock_gpu_baseline(dev, config="luna", steps=3, warmup=2):
+    """SURVEY 8d's second comparator, labelled separately from the CPU baseline: the reference's network as STOCK PyTorch modules
+    (nn.Conv3d / ConvTranspose3d / InstanceNorm3d / GroupNorm through cuDNN: the oracle's modules are the reference's operators) on
+    this GPU, the way the reference trains it (fp16 autocast + GradScaler = Lightning `precision: 16`, torch.optim.SGD nesterov,
+    cudnn.benchmark).  Network forward + backward + optimizer step ONLY, same batch shape -- no anchors, ATSS, sampling, box losses,
+    post-processing or NMS (a surrogate loss on the three outputs drives the backward), so the number FAVOURS the stock path."""
+    from oracle import model_oracle as mo
+    arch, anc, patch, bs = mo.make_plan(config)
+    cuda = torch.device(dev).type == "cuda"
+    old_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        torch.manual_seed(4321)
+        net = mo.RetinaUNetOracle(dict(arch), dict(anc)).to(dev)
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True, weight_decay=3e-5)
+        scaler = torch.amp.GradScaler("cuda", enabled=cuda)
+        images = torch.rand(bs, arch["in_channels"], *patch, device=dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast(device_type="cuda" if cuda else "cpu", dtype=torch.float16 if cuda else torch.bfloat16, enabled=cuda):
+                fm_all = net.decoder(net.encoder(images))
+                pred = net.head([fm_all[i] for i in net.decoder_levels])
+                seg = net.segmenter(fm_all)
+                loss = (pred["box_logits"].float().square().mean() + pred["box_deltas"].float().square().mean()
+                        + seg["seg_logits"].float().square().mean())
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+
+        for _ in range(warmup):
+            step()
+        if cuda:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        if cuda:
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+        else:
+            ms = 1e3 * (time.perf_counter() - t0) / steps
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30 if cuda else None
+        return {"value": bs / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kind": "stock PyTorch/cuDNN modules, fp16 autocast + GradScaler, NCDHW",
+                "sample": f"{steps} steps of batch {bs} {patch[0]}x{patch[1]}x{patch[2]}: network fwd + bwd + SGD only (no box engine / NMS; surrogate loss)",
+                "torch": torch.__version__, "cudnn": torch.backends.cudnn.version() if cuda else None, "max_memory_GiB": peak_gb}
+    finally:
+        torch.backends.cudnn.benchmark = old_bench
+        if cuda:
+            torch.cuda.empty_cache()
 
 
 def cpu_baseline():
