@@ -159,6 +159,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
+    ap.add_argument("--trace-layers", default=None, metavar="CSV",
+                    help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
+                         "(kernel chosen, layer geometry, ms, GFLOP per launch) -- maps the step time onto the network")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -271,6 +274,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+
+    if args.trace_layers and rank == 0:
+        conv_ops.trace_start()
+        step_resident(0)
+        rows = conv_ops.trace_dump(args.trace_layers)
+        print(f"[bench] wrote {rows} convolution launches of one train step to {args.trace_layers}", file=sys.stderr)
 
     # ---- roofline of the dominant kernel family (gather convolution), measured live with CUDA events
     roof = None

@@ -125,6 +125,12 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
 void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
+/* Profiling aid (off by default): one row per convolution-family launch -- kind (fprop | wgrad | first_*), the kernel the dispatch
+ * chose, the geometry, and the launch's duration from two CUDA events on its stream.  trace(1) clears + starts, trace(0) stops;
+ * trace_dump synchronises the device and writes CSV (idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop). */
+void nnd_conv_trace(int enable);
+long long nnd_conv_trace_count(void);
+int nnd_conv_trace_dump(const char* path);
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);

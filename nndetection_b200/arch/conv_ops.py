@@ -178,3 +178,17 @@ def set_stream_path(mode: int = 1, issuers: int = 2):
     """0: off, 1: streaming z-window tcgen05 kernel where profitable (default), 2: wherever the shape is supported."""
     L.lib().nnd_conv_set_stream_path(c_int(mode), c_int(issuers))
 
+
+
+def trace_start():
+    """Profiling aid: record one row per convolution-family launch (kernel chosen, layer geometry, duration) until `trace_dump`."""
+    L.lib().nnd_conv_trace(c_int(1))
+
+
+def trace_dump(path: str) -> int:
+    """Stop recording, synchronise, write the rows as CSV to `path`; returns the number of rows."""
+    lib = L.lib()
+    lib.nnd_conv_trace(c_int(0))
+    lib.nnd_conv_trace_count.restype = c_longlong
+    L.check(lib.nnd_conv_trace_dump(str(path).encode()), "nnd_conv_trace_dump")
+    return int(lib.nnd_conv_trace_count())

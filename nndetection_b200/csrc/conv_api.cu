@@ -4,6 +4,10 @@
 // (see conv_common.cuh for the gather-convolution form these numbers describe).
 #include "conv_common.cuh"
 
+#include <cstdio>
+#include <mutex>
+#include <vector>
+
 int nnd_conv_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
@@ -49,6 +53,37 @@ int parse_geom(const int* a, ConvGeom& g) {
 int g_force_igemm = 0;
 int g_wgrad_tc = 1;
 int g_stream = 1;
+
+// ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
+// ncu names kernels, not layers; this table is what maps the step time onto the network.
+struct TraceRec {
+  const char* kind;      // fprop | wgrad | first_fprop | first_wgrad   (dgrad launches are gather convolutions too: see T / strides)
+  const char* kernel;    // dispatch decision
+  int N, Di, Hi, Wi, Cin, Cout, Ld, Lh, Lw, sd, sh, sw, T;
+  cudaEvent_t e0, e1;
+};
+int g_trace_on = 0;
+std::vector<TraceRec> g_trace;
+std::mutex g_trace_mu;       // forward runs on the caller's thread, backward on autograd's worker thread
+
+struct TraceScope {
+  int idx = -1;
+  cudaStream_t st;
+  TraceScope(const char* kind, const char* kernel, const ConvGeom& g, int Cin, int Cout, cudaStream_t s) : st(s) {
+    if (!g_trace_on) return;
+    TraceRec r{kind, kernel, g.N, g.Di, g.Hi, g.Wi, Cin, Cout, g.Ld, g.Lh, g.Lw, g.sd, g.sh, g.sw, g.T, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace.push_back(r);
+    idx = (int)g_trace.size() - 1;
+  }
+  ~TraceScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    cudaEventRecord(g_trace[idx].e1, st);
+  }
+};
 }  // namespace
 
 extern "C" {
@@ -63,6 +98,37 @@ void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
 void nnd_conv_set_stream_path(int enable, int issuers) { g_stream = enable; nnd_conv_tcs_set_issuers(issuers); }
 
+// Profiling aid: nnd_conv_trace(1) clears the table and starts recording one row per convolution-family launch (two CUDA events
+// on the launch stream around it); nnd_conv_trace(0) stops.  nnd_conv_trace_dump synchronises the device and writes the rows as
+// CSV (idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop); returns NND_OK or NND_ERR_ARG / NND_ERR_CUDA.
+void nnd_conv_trace(int enable) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  if (enable) {
+    for (auto& r : g_trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_trace.clear();
+  }
+  g_trace_on = enable ? 1 : 0;
+}
+long long nnd_conv_trace_count() { return (long long)g_trace.size(); }
+int nnd_conv_trace_dump(const char* path) {
+  if (!path) return NND_ERR_ARG;
+  NND_CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  FILE* f = fopen(path, "w");
+  if (!f) return NND_ERR_ARG;
+  fprintf(f, "idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop\n");
+  for (size_t i = 0; i < g_trace.size(); ++i) {
+    const TraceRec& r = g_trace[i];
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { ms = -1.f; (void)cudaGetLastError(); }
+    const double gf = 2.0 * r.N * (double)r.Ld * r.Lh * r.Lw * r.T * r.Cin * r.Cout * 1e-9;
+    fprintf(f, "%zu,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.4f\n", i, r.kind, r.kernel, r.N, r.Di, r.Hi, r.Wi, r.Cin,
+            r.Cout, r.Ld, r.Lh, r.Lw, r.sd, r.sh, r.sw, r.T, ms, gf);
+  }
+  fclose(f);
+  return NND_OK;
+}
+
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st) {
@@ -74,10 +140,12 @@ int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* o
   ep.residual = (const __nv_bfloat16*)residual; ep.stat_sum = stat_sum; ep.stat_sq = stat_sq;
   if (!g_force_igemm && g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) {
     if (used_tc) *used_tc = 2;
+    TraceScope ts("fprop", "conv_tcs", g, g.Cin, Cout, st);
     return nnd_conv_tcs((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
   }
   const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
   if (used_tc) *used_tc = tc ? 1 : 0;
+  TraceScope ts("fprop", tc ? "conv_tc" : "conv_igemm", g, g.Cin, Cout, st);
   if (tc) return nnd_conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
   return nnd_conv_igemm((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
 }
@@ -86,11 +154,18 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
-  if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g)))
+  if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) {
+    TraceScope ts("wgrad", "wgrad_tc32", g, Cx, Cdy, st);
     return nnd_conv_wgrad_tc32((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
+  }
   // g_wgrad_tc: 1 = tcgen05 wgrad kernels (default), 2 = also the stacked 32-channel one on small volumes (tests), 4 = the
   // all-taps 128-output-channel kernel of conv_wgrad_tcn.cu (opt-in: measured SLOWER than the filter-row kernel, 0.38 vs
   // 0.23 ms at 32^3 x 4 -- its N = 48 MMAs cost 44 cycles for 24 cycles of math; kept as the A/B record of that experiment)
+  const char* wk = "wgrad_generic";
+  if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) wk = "wgrad_tcn";
+  else if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) wk = "wgrad_tc";
+  else if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx)) wk = "wgrad_halo";
+  TraceScope ts("wgrad", wk, g, Cx, Cdy, st);
   if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_tcn((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx))
@@ -104,12 +179,14 @@ int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom, in
                              float* stat_sq, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  TraceScope ts("first_fprop", "conv_first", g, g.Cin, Cout, st);
   return nnd_conv_first_fprop(x, w, g, Cout, (__nv_bfloat16*)out, stat_sum, stat_sq, st);
 }
 
 int nnd_conv_first_wgrad_f32(const float* x, const void* dy, const int* geom, int Cout, float* dw, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
+  TraceScope ts("first_wgrad", "conv_first", g, g.Cin, Cout, st);
   return nnd_conv_first_wgrad(x, (const __nv_bfloat16*)dy, g, Cout, dw, st);
 }
 
