@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
+    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 convs)")
     ap.add_argument("--trace-layers", default=None, metavar="CSV",
                     help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
                          "(kernel chosen, layer geometry, ms, GFLOP per launch) -- maps the step time onto the network")
@@ -192,6 +193,8 @@ def main():
     lib.nnd_launch_count.restype = __import__("ctypes").c_ulonglong
     if args.igemm_only:
         conv_ops.set_tensor_path(False)
+    if "wgrad_s2" in args.experimental.split(","):
+        conv_ops.set_wgrad_strided_tc(True)
     arch, anc, patch, bs = make_plan(args.config)
     torch.manual_seed(1234 + rank)
     net = RetinaUNetV001.from_config_plan(None, arch, anc).to(dev)
@@ -294,7 +297,7 @@ def main():
                "dtype": "bf16", "data": "synthetic",
                "config": {"workload": f"{args.config}: {patch[0]}x{patch[1]}x{patch[2]} {arch['in_channels']}ch, batch {bs}/GPU, "
                                       f"full train step (fwd+ATSS+HNM+losses+postprocess/3D-NMS+bwd+SGD)",
-                          "global_batch": bs * world, "parallelism": f"dp{world}",
+                          "global_batch": bs * world, "parallelism": f"dp{world}", "experimental": args.experimental,
                           "l2": f"{n_batches} distinct input batches; per-step activations (> 4 GB) exceed the 126 MB L2"},
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / args.steps},

@@ -180,6 +180,11 @@ def set_stream_path(mode: int = 1, issuers: int = 2):
 
 
 
+def set_wgrad_strided_tc(enable: bool):
+    """Opt-in: de-interleaved tcgen05 weight gradient for stride-2 convolutions (not yet validated on a device; default off)."""
+    L.lib().nnd_conv_set_wgrad_strided_tc(c_int(1 if enable else 0))
+
+
 def trace_start():
     """Profiling aid: record one row per convolution-family launch (kernel chosen, layer geometry, duration) until `trace_dump`."""
     L.lib().nnd_conv_trace(c_int(1))

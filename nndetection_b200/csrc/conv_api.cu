@@ -18,6 +18,7 @@ void nnd_conv_tcs_set_issuers(int n);
 int nnd_conv_wgrad(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                    long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tc_strided_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                       long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
 int nnd_conv_wgrad_tc32_supported(const ConvGeom& g, int Cdy, int Cx);
@@ -53,6 +54,7 @@ int parse_geom(const int* a, ConvGeom& g) {
 int g_force_igemm = 0;
 int g_wgrad_tc = 1;
 int g_stream = 1;
+int g_wgrad_strided = 0;
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
 // ncu names kernels, not layers; this table is what maps the step time onto the network.
@@ -93,6 +95,9 @@ void nnd_conv_set_tensor_path(int enable_tcgen05) { g_force_igemm = !enable_tcge
 // 1 (default): tcgen05 wgrad where eligible; 0: mma.sync halo wgrad (A/B); 2: also the stacked-tap 32-channel kernel on
 // volumes too small to fill the grid (tests)
 void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
+// 1: stride-2 convolutions take the de-interleaved tcgen05 wgrad (conv_wgrad_tc.cu, SW = 2) instead of the mma.sync kernels.
+// Default 0 until the variant has been validated on a B200 (it was written without one); tests/test_zz_experimental_gpu.py.
+void nnd_conv_set_wgrad_strided_tc(int enable) { g_wgrad_strided = enable; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -164,11 +169,14 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
   const char* wk = "wgrad_generic";
   if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) wk = "wgrad_tcn";
   else if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) wk = "wgrad_tc";
+  else if (!g_force_igemm && g_wgrad_tc && g_wgrad_strided && nnd_conv_wgrad_tc_strided_supported(g, Cdy, Cx)) wk = "wgrad_tc_s2";
   else if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx)) wk = "wgrad_halo";
   TraceScope ts("wgrad", wk, g, Cx, Cdy, st);
   if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_tcn((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx))
+    return nnd_conv_wgrad_tc((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
+  if (!g_force_igemm && g_wgrad_tc && g_wgrad_strided && nnd_conv_wgrad_tc_strided_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_tc((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   if (!g_force_igemm && nnd_conv_wgrad_halo_supported(g, Cdy, Cx))
     return nnd_conv_wgrad_halo((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);

@@ -11,13 +11,19 @@
 // N_T-channel ci tile, one contiguous range of voxel rows (split-K).  4 producer warps (cp.async, zero fill = padding)
 // -> 4-stage ring -> 3 issuer warps (one per dx tap, independent accumulators) -> 4 epilogue warps (tcgen05.ld ->
 // fp32 atomicAdd into dW, PyTorch weight layout).
+//
+// SW = 2 (opt-in until validated on the device, nnd_conv_set_wgrad_strided_tc): the same kernel for stride-2 convolutions,
+//   dW[tap][co][ci] = sum_o dy[o][co] * x[o * s + off_tap][ci].
+// dy rows are dense as before; an x row is loaded DE-INTERLEAVED: the 33 input voxels 2*w0 - 1 ... 2*w0 + 31 behind 16 outputs go
+// to two planes, "odd" (w = 2p - 1, p = 0..16, slots 0..16) and "even" (w = 2p, p = 0..15, slots 17..32), so that the operand
+// of tap dx is again 16 CONSECUTIVE 16-byte rows: dx = -1 -> odd plane from slot 0, dx = 0 -> even plane (slot 17), dx = +1 ->
+// odd plane from slot 1.  d / h strides only change which input row is fetched.
 #include "conv_common.cuh"
 #include "tcgen05.cuh"
 
 namespace {
 
 constexpr int RW = 16;                 // voxels per row segment (K of one MMA)
-constexpr int XW = RW + 2;             // x row with halo
 constexpr int ROWS = 4;                // row segments per pipeline stage
 constexpr int STAGES = 4;
 constexpr int M_T = 128;               // co tile (UMMA M); channels beyond Cdy are zero rows
@@ -30,7 +36,8 @@ struct WtArgs {
   const __nv_bfloat16* x; int Cx;
   float* dw; long long s_co, s_ci, s_tap;
   int Cout, Cin;
-  int N, D, H, W, wsegs;            // grid and row segments per h-row (ceil(W / 16))
+  int N, D, H, W, wsegs;            // dy grid and row segments per h-row (ceil(W / 16))
+  int Di, Hi, Wi, sd, sh;           // SW = 2 only: x grid and the d / h strides (w stride = SW)
   long long total_rows;             // N * D * H * wsegs
   long long rows_per_split;
   int n_groups;                     // filter rows (dz, dy)
@@ -39,9 +46,10 @@ struct WtArgs {
   int ci_tiles;
 };
 
-template <int N_T>
+template <int N_T, int SW>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc_kernel(const WtArgs a) {
+  constexpr int XW = SW == 1 ? RW + 2 : 2 * RW + 1;      // x row slots: 18 (halo row) or 17 + 16 (odd / even plane)
   constexpr int A_GROUPS = M_T / 8, B_GROUPS = N_T / 8;
   constexpr int A_GPITCH = ROWS * RW * 16;               // bytes between co groups inside a stage
   constexpr int B_GPITCH = ROWS * XW * 16;               // bytes between ci groups
@@ -113,7 +121,7 @@ conv_wgrad_tc_kernel(const WtArgs a) {
             cp_async16(dst, ok ? src : a.dy, ok);
             dst += 16; src += a.Cdy;
           }
-        } else {
+        } else if (SW == 1) {
           const int dd = d + dz, hh = h + dyo;
           row_ok = row_ok && (unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H;
           const __nv_bfloat16* src = a.x + ((((long long)n * a.D + dd) * a.H + hh) * a.W + (ws * RW - 1)) * a.Cx + ci0 + gidx * 8;
@@ -123,6 +131,19 @@ conv_wgrad_tc_kernel(const WtArgs a) {
             const bool ok = row_ok && (unsigned)(ws * RW - 1 + v) < (unsigned)a.W;
             cp_async16(dst, ok ? src : a.x, ok);
             dst += 16; src += a.Cx;
+          }
+        } else {
+          const int dd = d * a.sd + dz, hh = h * a.sh + dyo;
+          row_ok = row_ok && (unsigned)dd < (unsigned)a.Di && (unsigned)hh < (unsigned)a.Hi;
+          const int w_in0 = ws * RW * 2 - 1;                       // input voxel of slot v = 0 (odd plane, p = 0)
+          const __nv_bfloat16* src = a.x + ((((long long)n * a.Di + dd) * a.Hi + hh) * a.Wi + w_in0) * a.Cx + ci0 + gidx * 8;
+          const unsigned dst0 = sb + gidx * B_GPITCH + rr * (XW * 16);
+#pragma unroll
+          for (int v = 0; v < XW; ++v) {                           // v-th input voxel of the row: even v -> odd plane, odd v -> even plane
+            const bool ok = row_ok && (unsigned)(w_in0 + v) < (unsigned)a.Wi;
+            const int slot = (v & 1) ? (RW + 1) + (v >> 1) : (v >> 1);
+            cp_async16(dst0 + slot * 16, ok ? src : a.x, ok);
+            src += a.Cx;
           }
         }
       }
@@ -159,7 +180,10 @@ conv_wgrad_tc_kernel(const WtArgs a) {
         if (present) {
           const unsigned sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
           const unsigned long long a0 = make_desc(sa, 128, A_GPITCH);
-          const unsigned long long b0 = make_desc(sb + tap * 16, 128, B_GPITCH);
+          // start of the 16 voxel rows tap dx = tap - 1 reads: stride 1 -> the halo row shifted by tap; stride 2 -> odd plane
+          // (slot 0), even plane (slot 17), odd plane shifted by one (slot 1)
+          const unsigned tap_off = SW == 1 ? tap * 16 : (tap == 1 ? (RW + 1) * 16 : (tap >> 1) * 16);
+          const unsigned long long b0 = make_desc(sb + tap_off, 128, B_GPITCH);
 #pragma unroll
           for (int rr = 0; rr < ROWS; ++rr)
             tc_mma(d_tmem, a0 + (unsigned long long)((rr * RW * 16) >> 4), b0 + (unsigned long long)((rr * XW * 16) >> 4), IDESC,
@@ -205,8 +229,9 @@ conv_wgrad_tc_kernel(const WtArgs a) {
   }
 }
 
-template <int N_T>
+template <int N_T, int SW>
 int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
+  constexpr int XW = SW == 1 ? RW + 2 : 2 * RW + 1;
   const int co_tiles = (co_pad + M_T - 1) / M_T;
   a.ci_tiles = ci_pad / N_T;
   const long long tiles = (long long)a.n_groups * co_tiles * a.ci_tiles;
@@ -220,11 +245,11 @@ int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
   constexpr size_t SMEM = (size_t)STAGES * ((M_T / 8) * ROWS * RW * 16 + (N_T / 8) * ROWS * XW * 16) + 8 * (2 * STAGES + 1);
   static bool attr_set = false;
   if (!attr_set) {
-    NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<N_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<N_T, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
   dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(co_tiles * a.ci_tiles));
-  conv_wgrad_tc_kernel<N_T><<<grid, WG_THREADS, SMEM, st>>>(a);
+  conv_wgrad_tc_kernel<N_T, SW><<<grid, WG_THREADS, SMEM, st>>>(a);
   NND_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   return NND_OK;
 }
@@ -240,13 +265,26 @@ int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx) {
   return 1;
 }
 
+// Stride-2 (in w; 1 or 2 in d / h) convolutions with taps in [-1, 1]: the de-interleaved variant (SW = 2).
+int nnd_conv_wgrad_tc_strided_supported(const ConvGeom& g, int Cdy, int Cx) {
+  if (g.sw != 2 || g.sd < 1 || g.sd > 2 || g.sh < 1 || g.sh > 2) return 0;
+  if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
+  if (g.Do != g.Ld || g.Ho != g.Lh || g.Wo != g.Lw) return 0;
+  if (g.T < 9 || Cdy % 32 || Cx % 32 || Cdy < 64) return 0;
+  for (int t = 0; t < g.T; ++t)
+    if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
+  return 1;
+}
+
 int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                       long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
+  const bool strided = g.sw == 2;
   WtArgs a;
   a.dy = dy; a.Cdy = Cdy; a.x = x; a.Cx = Cx; a.dw = dw; a.s_co = s_co; a.s_ci = s_ci; a.s_tap = s_tap;
-  a.Cout = Cout; a.Cin = Cin; a.N = g.N; a.D = g.Di; a.H = g.Hi; a.W = g.Wi;
-  a.wsegs = (g.Wi + RW - 1) / RW;
-  a.total_rows = (long long)g.N * g.Di * g.Hi * a.wsegs;
+  a.Cout = Cout; a.Cin = Cin; a.N = g.N; a.D = g.Ld; a.H = g.Lh; a.W = g.Lw;      // dy grid (= the x grid at stride 1)
+  a.Di = g.Di; a.Hi = g.Hi; a.Wi = g.Wi; a.sd = g.sd; a.sh = g.sh;
+  a.wsegs = (g.Lw + RW - 1) / RW;
+  a.total_rows = (long long)g.N * g.Ld * g.Lh * a.wsegs;
   if (a.total_rows <= 0) return NND_OK;
   a.n_groups = 0;
   for (int z = -1; z <= 1; ++z)
@@ -261,7 +299,12 @@ int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, 
         ++a.n_groups;
       }
     }
-  if (Cx % 128 == 0) return launch_wt<128>(a, Cdy, Cx, st);
-  if (Cx % 64 == 0) return launch_wt<64>(a, Cdy, Cx, st);
-  return launch_wt<32>(a, Cdy, Cx, st);
+  if (strided) {
+    if (Cx % 128 == 0) return launch_wt<128, 2>(a, Cdy, Cx, st);
+    if (Cx % 64 == 0) return launch_wt<64, 2>(a, Cdy, Cx, st);
+    return launch_wt<32, 2>(a, Cdy, Cx, st);
+  }
+  if (Cx % 128 == 0) return launch_wt<128, 1>(a, Cdy, Cx, st);
+  if (Cx % 64 == 0) return launch_wt<64, 1>(a, Cdy, Cx, st);
+  return launch_wt<32, 1>(a, Cdy, Cx, st);
 }

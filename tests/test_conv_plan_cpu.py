@@ -114,3 +114,41 @@ def test_plan_geometry_reproduces_torch_weight_gradient(k, s, transposed):
     ref = w.grad.numpy().reshape(w.shape[0], w.shape[1], T)
     ref = np.transpose(ref, (2, 1, 0)) if transposed else np.transpose(ref, (2, 0, 1))      # -> [tap][co][ci]
     np.testing.assert_allclose(dw, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("s,shape", [((2, 2, 2), (2, 7, 9, 40)), ((1, 2, 2), (1, 4, 6, 13)), ((2, 2, 2), (1, 5, 4, 34))])
+def test_deinterleaved_row_layout_of_the_strided_wgrad_kernel(s, shape):
+    """Index arithmetic of conv_wgrad_tc.cu, SW = 2, emulated in numpy (the MMA itself is the validated stride-1 machinery): a row of
+    16 outputs loads the 33 input voxels 2*w0 - 1 .. 2*w0 + 31 into slots [odd plane 0..16 | even plane 17..32] (even v -> slot v/2,
+    odd v -> 17 + v/2), tap dx reads 16 consecutive slots from 0 / 17 / 1 -- summed over rows this must be torch's weight gradient."""
+    RW, XW = 16, 33
+    N, D, H, W = shape
+    cin, cout = 3, 4
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, cin, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv3d(x, w, stride=s, padding=1)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    Ld, Lh, Lw = y.shape[2:]
+    xn, dyn = x.numpy(), gy.numpy()
+    dw = np.zeros((cout, cin, 3, 3, 3))
+    wsegs = -(-Lw // RW)
+    tap_start = {0: 0, 1: RW + 1, 2: 1}                                   # slot where tap dx = k - 1 starts
+    for n, d, h, ws in itertools.product(range(N), range(Ld), range(Lh), range(wsegs)):
+        A = np.zeros((RW, cout))
+        for v in range(RW):
+            if ws * RW + v < Lw:
+                A[v] = dyn[n, :, d, h, ws * RW + v]
+        for dz, dyo in itertools.product((-1, 0, 1), repeat=2):
+            dd, hh = d * s[0] + dz, h * s[1] + dyo
+            B = np.zeros((XW, cin))
+            if 0 <= dd < D and 0 <= hh < H:
+                w_in0 = ws * RW * 2 - 1
+                for v in range(XW):
+                    if 0 <= w_in0 + v < W:
+                        slot = (RW + 1) + (v >> 1) if (v & 1) else (v >> 1)
+                        B[slot] = xn[n, :, dd, hh, w_in0 + v]
+            for k in range(3):
+                dw[:, :, dz + 1, dyo + 1, k] += A.T @ B[tap_start[k]:tap_start[k] + RW]
+    assert np.allclose(dw, w.grad.numpy(), rtol=1e-10, atol=1e-10)

@@ -1,0 +1,56 @@
+"""Kernels written WITHOUT a GPU at the end of round 1 (budget spent), switched off in the product until validated.  These tests
+switch them on; because an addressing bug in a tcgen05 kernel can poison the CUDA context for everything that follows, they only
+run when NND_EXPERIMENTAL=1 (scripts/gpu_checkup.sh runs them in their own process after the regular suite).
+
+  * nnd_conv_set_wgrad_strided_tc(1): weight gradient of stride-2 3x3x3 convolutions on tcgen05 (conv_wgrad_tc.cu, SW = 2: x rows
+    de-interleaved into an odd and an even plane so every tap is again 16 consecutive 16-byte rows)."""
+import os
+from ctypes import c_int
+
+import pytest
+import torch
+
+import tutil as util  # noqa: F401
+from test_net_gpu import make_pair, q, rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NND_EXPERIMENTAL") != "1", reason="unvalidated kernels: set NND_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("cin,cout,s,shape", [
+    (32, 64, 2, (2, 12, 16, 40)),           # W = 40 -> 20 outputs: two row segments, the second one 4 wide
+    (64, 128, (1, 2, 2), (2, 6, 12, 12)),   # LIDC-style first stride, 6 outputs per row
+    (128, 256, 2, (1, 8, 10, 34)),          # two co tiles, odd output width (17)
+    (256, 320, 2, (2, 8, 8, 8)),            # two ci tiles, three co tiles (the last one half empty)
+    (32, 64, 2, (1, 9, 11, 13)),            # odd input sizes in every axis
+])
+def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
+    """fp32 dW against the CPU oracle on bf16-exact operands (5e-3) and against the mma.sync kernels (accumulation order: 1e-3)."""
+    from nndetection_b200 import _lib as L
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair("instance", cin, cout, 3, s, norm=False)
+    g = torch.Generator().manual_seed(61)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res, kernels = {}, {}
+    lib = L.lib()
+    try:
+        for mode in (1, 0):
+            lib.nnd_conv_set_wgrad_strided_tc(c_int(mode))
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            ops.trace_start()
+            mine(xm).backward(gy.cuda().to(torch.bfloat16))
+            import csv, tempfile
+            with tempfile.TemporaryDirectory() as td:
+                ops.trace_dump(os.path.join(td, "t.csv"))
+                kernels[mode] = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
+            res[mode] = mine.conv.weight.grad.cpu().clone()
+    finally:
+        lib.nnd_conv_set_wgrad_strided_tc(c_int(0))
+    assert kernels[1] == ["wgrad_tc_s2"] and kernels[0] != ["wgrad_tc_s2"]
+    assert rel_err(res[1], ref.conv.weight.grad) < 5e-3
+    assert rel_err(res[1], res[0]) < 1e-3
