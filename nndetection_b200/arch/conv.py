@@ -159,8 +159,13 @@ class _ConvBlockFn(torch.autograd.Function):
             ops.conv_first_wgrad(x, dy, plan.fprop[0], cout, dw)
         else:
             s_co, s_ci = (T, cout * T) if conv.transposed else (cin * T, T)
-            for g in plan.wgrad:
-                ops.conv_wgrad(dy, cout, x, cin, g, dw, s_co, s_ci, 1, cout, cin)
+            if (conv.transposed and ops.wgrad_strided_tc_enabled() and plan.s[2] == 2 and cin >= 64 and cin % 32 == 0
+                    and cout % 32 == 0):
+                # opt-in: one strided gather with the roles swapped (dense = x, strided = dy) instead of one launch per tap
+                ops.conv_wgrad(x, cin, dy, cout, plan.wgrad_swapped, dw, s_ci, s_co, 1, cin, cout)
+            else:
+                for g in plan.wgrad:
+                    ops.conv_wgrad(dy, cout, x, cin, g, dw, s_co, s_ci, 1, cout, cin)
         dx = None
         if ctx.needs_input_grad[0] and not layer.is_first:
             _, wp_b = layer.packed()

@@ -97,6 +97,9 @@ class ConvPlan:
             self.dgrad = [_geom(N, self.out_sp, cdy, in_sp, s, in_sp, (1, 1, 1), (0, 0, 0), taps)]
             self.dgrad_covers_all = True
             self.wgrad = self.fprop
+            # the same weight gradient as ONE strided gather with the operands' roles swapped: dense operand = the layer input,
+            # strided operand = dy read at s * i + tap (used by the opt-in tcgen05 path, arch/conv.py)
+            self.wgrad_swapped = self.dgrad[0]
 
 
 
@@ -180,9 +183,19 @@ def set_stream_path(mode: int = 1, issuers: int = 2):
 
 
 
+_WGRAD_STRIDED_TC = False
+
+
 def set_wgrad_strided_tc(enable: bool):
-    """Opt-in: de-interleaved tcgen05 weight gradient for stride-2 convolutions (not yet validated on a device; default off)."""
+    """Opt-in: de-interleaved tcgen05 weight gradient for stride-2 convolutions and kernel == stride transposed convolutions
+    (not yet validated on a device; default off)."""
+    global _WGRAD_STRIDED_TC
     L.lib().nnd_conv_set_wgrad_strided_tc(c_int(1 if enable else 0))
+    _WGRAD_STRIDED_TC = bool(enable)
+
+
+def wgrad_strided_tc_enabled() -> bool:
+    return _WGRAD_STRIDED_TC
 
 
 def trace_start():

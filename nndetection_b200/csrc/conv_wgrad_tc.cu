@@ -265,12 +265,14 @@ int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx) {
   return 1;
 }
 
-// Stride-2 (in w; 1 or 2 in d / h) convolutions with taps in [-1, 1]: the de-interleaved variant (SW = 2).
+// Stride-2 (in w; 1 or 2 in d / h) convolutions with taps in [-1, 1]: the de-interleaved variant (SW = 2).  Also serves the
+// weight gradient of kernel == stride transposed convolutions with the operands' roles swapped by the caller (dense operand =
+// the layer input, strided operand = dy read at 2i + {0, 1}: taps (0 / 1, 0 / 1, 0 / 1), arch/conv.py).
 int nnd_conv_wgrad_tc_strided_supported(const ConvGeom& g, int Cdy, int Cx) {
   if (g.sw != 2 || g.sd < 1 || g.sd > 2 || g.sh < 1 || g.sh > 2) return 0;
   if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
   if (g.Do != g.Ld || g.Ho != g.Lh || g.Wo != g.Lw) return 0;
-  if (g.T < 9 || Cdy % 32 || Cx % 32 || Cdy < 64) return 0;
+  if (g.T < 4 || Cdy % 32 || Cx % 32 || Cdy < 64) return 0;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
   return 1;

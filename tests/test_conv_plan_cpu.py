@@ -152,3 +152,50 @@ def test_deinterleaved_row_layout_of_the_strided_wgrad_kernel(s, shape):
             for k in range(3):
                 dw[:, :, dz + 1, dyo + 1, k] += A.T @ B[tap_start[k]:tap_start[k] + RW]
     assert np.allclose(dw, w.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("s,shape", [((2, 2, 2), (2, 3, 5, 20)), ((1, 2, 2), (1, 4, 3, 7))])
+def test_deinterleaved_row_layout_serves_transposed_conv_weight_gradient(s, shape):
+    """Same kernel arithmetic with the operands' roles swapped (arch/conv.py, opt-in path): rows run over the layer INPUT grid (dense
+    operand x), the strided operand is dy read at s * i + tap with taps in {0, 1}: group offsets (dz, dy) in {0, 1}^2, tap dx = 0 ->
+    even plane (slot 17), dx = 1 -> odd plane from slot 1.  Must equal torch's ConvTranspose3d weight gradient [Cin, Cout, k, k, k]."""
+    RW, XW = 16, 33
+    N, D, H, W = shape
+    cin, cout = 4, 3
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(N, cin, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cin, cout, *s, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose3d(x, w, stride=s)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    Do, Ho, Wo = y.shape[2:]
+    xn, dyn = x.numpy(), gy.numpy()
+    dw = np.zeros((cin, cout, *s))
+    wsegs = -(-W // RW)
+    tap_start = {0: RW + 1, 1: 1}                                         # off_w = 0 -> even plane, +1 -> odd plane shifted
+    for n, d, h, ws in itertools.product(range(N), range(D), range(H), range(wsegs)):
+        A = np.zeros((RW, cin))
+        for v in range(RW):
+            if ws * RW + v < W:
+                A[v] = xn[n, :, d, h, ws * RW + v]
+        for dz, dyo in itertools.product(range(s[0]), range(s[1])):
+            dd, hh = d * s[0] + dz, h * s[1] + dyo
+            B = np.zeros((XW, cout))
+            if 0 <= dd < Do and 0 <= hh < Ho:
+                w_in0 = ws * RW * 2 - 1
+                for v in range(XW):
+                    if 0 <= w_in0 + v < Wo:
+                        slot = (RW + 1) + (v >> 1) if (v & 1) else (v >> 1)
+                        B[slot] = dyn[n, :, dd, hh, w_in0 + v]
+            for dx in range(2):
+                dw[:, :, dz, dyo, dx] += A.T @ B[tap_start[dx]:tap_start[dx] + RW]
+    assert np.allclose(dw, w.grad.numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_transposed_plan_exposes_the_swapped_weight_gradient_geometry():
+    """ConvPlan.wgrad_swapped: a single gather geometry over the INPUT grid reading the output grid at s * i + tap, all k^3 taps."""
+    plan = ConvPlan(2, 64, 32, (4, 6, 8), 2, 2, 0, True)
+    g = list(plan.wgrad_swapped)
+    assert g[:21] == [2, 8, 12, 16, 32, 4, 6, 8, 2, 2, 2, 4, 6, 8, 1, 1, 1, 0, 0, 0, 8]
+    taps = [tuple(g[21 + 4 * t: 25 + 4 * t]) for t in range(8)]
+    assert taps == [(a, b, c, (a * 2 + b) * 2 + c) for a, b, c in itertools.product(range(2), repeat=3)]

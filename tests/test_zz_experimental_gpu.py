@@ -39,7 +39,7 @@ def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
     lib = L.lib()
     try:
         for mode in (1, 0):
-            lib.nnd_conv_set_wgrad_strided_tc(c_int(mode))
+            ops.set_wgrad_strided_tc(bool(mode))
             mine.zero_grad(set_to_none=True)
             xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
             ops.trace_start()
@@ -50,7 +50,40 @@ def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
                 kernels[mode] = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
-        lib.nnd_conv_set_wgrad_strided_tc(c_int(0))
+        ops.set_wgrad_strided_tc(False)
     assert kernels[1] == ["wgrad_tc_s2"] and kernels[0] != ["wgrad_tc_s2"]
     assert rel_err(res[1], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[1], res[0]) < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,s,shape", [(64, 32, 2, (2, 4, 6, 40)), (128, 64, 2, (1, 5, 3, 9)), (128, 128, (1, 2, 2), (1, 4, 4, 4)),
+                                             (128, 128, 2, (2, 2, 2, 2))])
+def test_transposed_conv_wgrad_on_tcgen05(cin, cout, s, shape):
+    """Up-convolutions (kernel == stride): ONE strided launch with the operands' roles swapped instead of one launch per tap."""
+    from nndetection_b200 import _lib as L  # noqa: F401
+    from nndetection_b200.arch import conv_ops as ops
+    import csv, tempfile
+    mine, ref = make_pair("instance", cin, cout, None, s, transposed=True)
+    g = torch.Generator().manual_seed(62)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res, kernels = {}, {}
+    try:
+        for mode in (True, False):
+            ops.set_wgrad_strided_tc(mode)
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            ops.trace_start()
+            mine(xm).backward(gy.cuda().to(torch.bfloat16))
+            with tempfile.TemporaryDirectory() as td:
+                ops.trace_dump(os.path.join(td, "t.csv"))
+                kernels[mode] = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
+            res[mode] = mine.conv.weight.grad.cpu().clone()
+    finally:
+        ops.set_wgrad_strided_tc(False)
+    assert kernels[True] == ["wgrad_tc_s2"] and len(kernels[False]) == (8 if s == 2 else 4)
+    assert rel_err(res[True], ref.conv.weight.grad) < 5e-3
+    assert rel_err(res[True], res[False]) < 1e-3
