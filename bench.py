@@ -400,13 +400,13 @@ def stock_gpu_baseline(dev, config="luna", steps=3, warmup=2):
     """SURVEY 8d's second comparator, labelled separately from the CPU baseline: the reference's network as STOCK PyTorch modules
     (nn.Conv3d / ConvTranspose3d / InstanceNorm3d / GroupNorm through cuDNN: the oracle's modules are the reference's operators) on
     this GPU, the way the reference trains it (fp16 autocast + GradScaler = Lightning `precision: 16`, torch.optim.SGD nesterov,
-    cudnn.benchmark).  Network forward + backward + optimizer step ONLY, same batch shape -- no anchors, ATSS, sampling, box losses,
+    cudnn.benchmark off = nndet/conf/train/v001.yaml:39, which also keeps this leg free of minutes of cuDNN autotuning).  Network forward + backward + optimizer step ONLY, same batch shape -- no anchors, ATSS, sampling, box losses,
     post-processing or NMS (a surrogate loss on the three outputs drives the backward), so the number FAVOURS the stock path."""
     from oracle import model_oracle as mo
     arch, anc, patch, bs = mo.make_plan(config)
     cuda = torch.device(dev).type == "cuda"
     old_bench = torch.backends.cudnn.benchmark
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = False
     try:
         torch.manual_seed(4321)
         net = mo.RetinaUNetOracle(dict(arch), dict(anc)).to(dev)
@@ -442,7 +442,7 @@ def stock_gpu_baseline(dev, config="luna", steps=3, warmup=2):
         else:
             ms = 1e3 * (time.perf_counter() - t0) / steps
         peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30 if cuda else None
-        return {"value": bs / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kind": "stock PyTorch/cuDNN modules, fp16 autocast + GradScaler, NCDHW",
+        return {"value": bs / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kind": "stock PyTorch/cuDNN modules, fp16 autocast + GradScaler, NCDHW, cudnn.benchmark off (reference default)",
                 "sample": f"{steps} steps of batch {bs} {patch[0]}x{patch[1]}x{patch[2]}: network fwd + bwd + SGD only (no box engine / NMS; surrogate loss)",
                 "torch": torch.__version__, "cudnn": torch.backends.cudnn.version() if cuda else None, "max_memory_GiB": peak_gb}
     finally:
