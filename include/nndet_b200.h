@@ -121,10 +121,11 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
  *      (csrc/conv_common.cuh): N,Di,Hi,Wi,Cin, Ld,Lh,Lw, sd,sh,sw, Do,Ho,Wo, omd,omh,omw, ood,ooh,oow, T, then per tap
  *      (off_d, off_h, off_w, weight_tap).  w: bf16 [T][CoutPad][Cin] from nnd_pack_weights.  Epilogue: +bias, +residual,
  *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
- *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel. */
+ *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel, 3 tcgen05 stride-2 tile kernel (opt-in). */
 void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_wgrad_strided_tc(int enable);       /* opt-in (default 0): de-interleaved tcgen05 wgrad for stride-2 convolutions, not yet validated on a device */
+void nnd_conv_set_gather_strided_tc(int enable);      /* opt-in (default 0): de-interleaved-halo tcgen05 kernel for stride-2 gathers, not yet validated on a device */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
 /* Profiling aid (off by default): one row per convolution-family launch -- kind (fprop | wgrad | first_*), the kernel the dispatch
  * chose, the geometry, and the launch's duration from two CUDA events on its stream.  trace(1) clears + starts, trace(0) stops;

@@ -194,6 +194,12 @@ def set_wgrad_strided_tc(enable: bool):
     _WGRAD_STRIDED_TC = bool(enable)
 
 
+def set_gather_strided_tc(enable: bool):
+    """Opt-in: de-interleaved-halo tcgen05 kernel for stride-2 convolutions and the dgrad of up-convolutions (not yet validated on
+    a device; default off)."""
+    L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
+
+
 def wgrad_strided_tc_enabled() -> bool:
     return _WGRAD_STRIDED_TC
 

@@ -11,6 +11,8 @@
 int nnd_conv_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tc_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tcs_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tcs_profitable(const ConvGeom& g, const ConvEpilogue& ep);
@@ -55,6 +57,7 @@ int g_force_igemm = 0;
 int g_wgrad_tc = 1;
 int g_stream = 1;
 int g_wgrad_strided = 0;
+int g_gather_strided = 0;
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
 // ncu names kernels, not layers; this table is what maps the step time onto the network.
@@ -98,6 +101,9 @@ void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
 // 1: stride-2 convolutions take the de-interleaved tcgen05 wgrad (conv_wgrad_tc.cu, SW = 2) instead of the mma.sync kernels.
 // Default 0 until the variant has been validated on a B200 (it was written without one); tests/test_zz_experimental_gpu.py.
 void nnd_conv_set_wgrad_strided_tc(int enable) { g_wgrad_strided = enable; }
+// 1: stride-2 gathers (3x3x3 stride-2 convolutions, dgrad of up-convolutions) take the de-interleaved-halo tcgen05 tile kernel
+// (conv_tc.cu, S2 = 1) instead of the mma.sync kernel.  Default 0 until validated on a B200 (written without one).
+void nnd_conv_set_gather_strided_tc(int enable) { g_gather_strided = enable; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -147,6 +153,11 @@ int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* o
     if (used_tc) *used_tc = 2;
     TraceScope ts("fprop", "conv_tcs", g, g.Cin, Cout, st);
     return nnd_conv_tcs((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+  }
+  if (!g_force_igemm && g_gather_strided && nnd_conv_tc_s2_supported(g, ep)) {
+    if (used_tc) *used_tc = 3;
+    TraceScope ts("fprop", "conv_tc_s2", g, g.Cin, Cout, st);
+    return nnd_conv_tc_s2((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
   }
   const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
   if (used_tc) *used_tc = tc ? 1 : 0;

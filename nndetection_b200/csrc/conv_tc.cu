@@ -18,6 +18,13 @@
 // fence.proxy.async -> mbarrier), MT issuer warps (lane 0 issues tcgen05.mma / tcgen05.commit for its depth slice), 4 epilogue warps
 // (tcgen05.ld -> bias / residual / scale -> bf16 -> 64-byte row stores, per-(sample, channel) norm statistics via a
 // warp transpose-reduce).  Persistent grid = #SMs, static round-robin tiles.
+//
+// S2 = 1 (opt-in until validated on the device, nnd_conv_set_gather_strided_tc): the same kernel for stride-2 gathers (3x3x3
+// stride-2 convolutions, and the 2x2x2 stride-2 convolution that is the dgrad of an up-convolution).  Input position = 2 * lo +
+// off with off in [-1, 1]; the halo of a tile is staged DE-INTERLEAVED per axis -- "odd" plane (positions 2p - 1, p = 0..n) in slots
+// 0..n, "even" plane (2p, p = 0..n-1) in slots n+1..2n -- so that the 8 (w) x 16 (h) x MT (d) voxels a tap multiplies are again
+// consecutive slots: off = -1 -> slot 0, off = 0 -> slot n + 1, off = +1 -> slot 1 of that axis.  16 channels per chunk
+// (the halo is 8x the tile instead of 1.7x), one K = 16 MMA per tap and depth slice.
 #include "conv_common.cuh"
 #include "tcgen05.cuh"
 
@@ -40,11 +47,15 @@ struct TcTiles {
 
 
 // TG = taps per pipeline item (weight slices loaded / consumed together), ACC = TMEM accumulator stages
-template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS>
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2>
 __global__ void __launch_bounds__(tc_threads(MT), 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
                const ConvEpilogue ep, const TcTiles tl) {
-  constexpr int HALO_SLICES = MT + 2;
+  // stride-1 names of the namespace constants are shadowed by their per-variant values
+  constexpr int KG = S2 ? 2 : ::KG;                          // channel groups of 8 per chunk
+  constexpr int HY = S2 ? 2 * BH + 1 : ::HY, HX = S2 ? 2 * BW + 1 : ::HX;
+  constexpr int ROW_PITCH = HX * 16, SLICE_PITCH = HY * ROW_PITCH;
+  constexpr int HALO_SLICES = S2 ? 2 * MT + 1 : MT + 2;
   constexpr int HV = HALO_SLICES * HY * HX;                 // halo voxels per channel group
   constexpr int A_BYTES = KG * HV * 16;
   constexpr int B_TAP_BYTES = N_TILE * KG * 16;            // one tap slice [kg][n][8]
@@ -73,7 +84,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   auto TEMPTY = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + 2 + i); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KC = g.Cin / 32, T = g.T;
+  const int KC = g.Cin / (8 * KG), T = g.T;
 
   if (tid == 0) {
     for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD / 32); mbar_init(EMPTYB(i), MT); }
@@ -81,7 +92,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
     for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), MT); mbar_init(TEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < T) s_tapoff[tid] = (((g.off_d[tid] + 1) * HY + (g.off_h[tid] + 1)) * HX + (g.off_w[tid] + 1)) * 16;
+  if (S2) {
+    // slot of output 0 on an axis with n outputs per tile: odd plane first (n + 1 slots), then the even plane
+    auto sl = [](int off, int n) { return off == 0 ? n + 1 : (off > 0 ? 1 : 0); };
+    if (tid < T) s_tapoff[tid] = ((sl(g.off_d[tid], MT) * HY + sl(g.off_h[tid], BH)) * HX + sl(g.off_w[tid], BW)) * 16;
+  } else {
+    if (tid < T) s_tapoff[tid] = (((g.off_d[tid] + 1) * HY + (g.off_h[tid] + 1)) * HX + (g.off_w[tid] + 1)) * 16;
+  }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -134,10 +151,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
         mbar_wait_warp(EMPTYA(astage), a_phase ^ 1, lane);
       }
       const unsigned a_base = smem_u32(sA + astage * A_BYTES);
-      const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin + kc * 32;
+      const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin + kc * (8 * KG);
       for (int rr = tid; rr < HROWS; rr += NUM_PROD) {
         const int gidx = rr / (HALO_SLICES * HY); const int r2 = rr - gidx * (HALO_SLICES * HY);
         const int z = r2 / HY, y = r2 - z * HY;
+        if (!S2) {
         const int d = d0 - 1 + z, h = h0 - 1 + y;
         const bool row_ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
         const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + (w0 - 1)) * g.Cin + gidx * 8;
@@ -148,6 +166,22 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
           cp_async16(dst, ok ? src : in, ok);
           dst += 16; src += g.Cin;
         }
+        } else {
+          // slot -> input position: odd plane slot p -> 2 (o0 + p) - 1, even plane slot n + 1 + p -> 2 (o0 + p)
+          const int d = z <= MT ? 2 * (d0 + z) - 1 : 2 * (d0 + z - (MT + 1));
+          const int h = y <= BH ? 2 * (h0 + y) - 1 : 2 * (h0 + y - (BH + 1));
+          const bool row_ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
+          const int w_in0 = 2 * w0 - 1;
+          const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + w_in0) * g.Cin + gidx * 8;
+          const unsigned dst0 = a_base + rr * (HX * 16);
+#pragma unroll
+          for (int v = 0; v < HX; ++v) {                 // v-th input voxel of the row: even v -> odd plane, odd v -> even plane
+            const bool ok = row_ok && (unsigned)(w_in0 + v) < (unsigned)g.Wi;
+            const int slot = (v & 1) ? (BW + 1) + (v >> 1) : (v >> 1);
+            cp_async16(dst0 + slot * 16, ok ? src : in, ok);
+            src += g.Cin;
+          }
+        }
       }
       astage ^= 1; if (astage == 0) a_phase ^= 1;
     };
@@ -156,7 +190,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const int tile = blockIdx.x + (chunk / KC) * gridDim.x;
       const int kc = chunk % KC;
       const int nt = tile % tl.NT;
-      const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * 32;
+      const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * (8 * KG);
       for (int it = 0; it < NI_ITEMS; ++it) {
         mbar_wait_warp(EMPTYB(slot), slot_phase ^ 1, lane);
         if (chunk == 0 && it == 0) load_halo(0);
@@ -214,7 +248,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
               const unsigned long long b_desc0 = b_item + (unsigned long long)((tt * B_TAP_BYTES) >> 4);
               const unsigned long long a_tap = a_desc0 + (unsigned long long)(s_tapoff[it * TG + tt] >> 4);
               tc_mma(d_tmem, a_tap, b_desc0, IDESC, (kc | it | tt) != 0 ? 1u : 0u);
-              tc_mma(d_tmem, a_tap + (unsigned long long)((2 * LBO_A) >> 4), b_desc0 + (unsigned long long)((2 * LBO_B) >> 4), IDESC, 1u);
+              if (KG == 4)
+                tc_mma(d_tmem, a_tap + (unsigned long long)((2 * LBO_A) >> 4), b_desc0 + (unsigned long long)((2 * LBO_B) >> 4), IDESC, 1u);
             }
             tc_commit(EMPTYB(slot));
             if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
@@ -343,20 +378,22 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   }
 }
 
-template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS>
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2 = 0>
 int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+  constexpr int KG = S2 ? 2 : ::KG;
+  constexpr int HY = S2 ? 2 * BH + 1 : ::HY, HX = S2 ? 2 * BW + 1 : ::HX;
   TcTiles tl;
   tl.DB = (g.Ld + MT - 1) / MT; tl.HB = (g.Lh + BH - 1) / BH; tl.WB = (g.Lw + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
   tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
-  constexpr int HV = (MT + 2) * HY * HX;
+  constexpr int HV = (S2 ? 2 * MT + 1 : MT + 2) * HY * HX;
   const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
   static bool attr_set = false;
   if (!attr_set) {
-    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
-  conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
+  conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
   NND_LAUNCH_CHECK("conv_tc_kernel");
   return NND_OK;
 }
@@ -383,6 +420,29 @@ int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
   }
   if (g.Lh < 8 || g.Lw < 8) return 0;
   return 1;
+}
+
+// Stride-2 gathers (S2 variant): 3x3x3 stride-2 convolutions and the 2x2x2 stride-2 convolution behind an up-convolution's dgrad.
+int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep) {
+  if (g.sd != 2 || g.sh != 2 || g.sw != 2) return 0;
+  if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
+  if (g.Ld != g.Do || g.Lh != g.Ho || g.Lw != g.Wo) return 0;
+  if (g.T < 8 || g.Cin % 16) return 0;
+  for (int t = 0; t < g.T; ++t)
+    if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
+  if (ep.out_fp32 || ep.Cout % 32 || ep.CoutPad != ep.Cout) return 0;
+  if (ep.out_v_stride != ep.Cout || ep.out_n_stride != (long long)g.Do * g.Ho * g.Wo * ep.Cout) return 0;
+  if (g.Lh < 8 || g.Lw < 8) return 0;
+  return 1;
+}
+
+int nnd_conv_tc_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+  if (!nnd_conv_tc_s2_supported(g, ep)) return NND_ERR_ARG;
+  const bool g3 = g.T % 3 == 0;
+  // two depth slices per tile: the de-interleaved halo of 16 channels (5 x 33 x 17 voxels) is 88 KB per stage
+  if (ep.CoutPad % 128 == 0) return g3 ? launch_tc<128, 2, 3, 2, 3, 1>(in, w, g, ep, st) : launch_tc<128, 2, 1, 2, 8, 1>(in, w, g, ep, st);
+  if (ep.CoutPad % 64 == 0) return g3 ? launch_tc<64, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tc<64, 2, 1, 2, 8, 1>(in, w, g, ep, st);
+  return g3 ? launch_tc<32, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tc<32, 2, 1, 2, 8, 1>(in, w, g, ep, st);
 }
 
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {

@@ -10,8 +10,9 @@ timeout 600 python -m pytest tests -q -m gpu -rxX 2>&1 | tail -40 > gpurun_out/p
 timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 240 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --trace-layers gpurun_out/layers.csv > gpurun_out/bench_trace.json 2>> gpurun_out/bench.err
 # kernels written without a GPU (off by default): their tests in a process of their own, then an A/B bench line
-NND_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_zz_experimental_gpu.py -q -x 2>&1 | tail -15 > gpurun_out/pytest_experimental.log
+NND_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_experimental_gpu.py -q 2>&1 | tail -15 > gpurun_out/pytest_experimental.log
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2 > gpurun_out/bench_wgrad_s2.json 2>> gpurun_out/bench.err
+timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2,gather_s2 > gpurun_out/bench_s2_all.json 2>> gpurun_out/bench.err
 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -s 2150 -c 900 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --profile > gpurun_out/profile.log 2>&1
 python - <<'PY'
@@ -28,4 +29,4 @@ with open("gpurun_out/layers_summary.txt", "w") as f:
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         f.write(f"{v[0]:7.3f} {100 * v[0] / tot:6.2f} {v[2]:3d} {v[1] / max(v[0], 1e-9):8.1f}  {k[0]:12s} {k[1]:14s} {k[2]:>3s}->{k[3]:<4s} {k[4]:11s} {k[5]:6s} {k[6]}\n")
 PY
-tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
+tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt

@@ -199,3 +199,66 @@ def test_transposed_plan_exposes_the_swapped_weight_gradient_geometry():
     assert g[:21] == [2, 8, 12, 16, 32, 4, 6, 8, 2, 2, 2, 4, 6, 8, 1, 1, 1, 0, 0, 0, 8]
     taps = [tuple(g[21 + 4 * t: 25 + 4 * t]) for t in range(8)]
     assert taps == [(a, b, c, (a * 2 + b) * 2 + c) for a, b, c in itertools.product(range(2), repeat=3)]
+
+
+def _emulate_s2_tile_kernel(x, w_taps, offs, out_sp, MT=2, BH=16, BW=8):
+    """Index arithmetic of conv_tc.cu, S2 = 1 in numpy: per tile (MT x 16 x 8 outputs) the halo is staged de-interleaved per axis
+    (odd plane: slots 0..n <- positions 2 (o0 + p) - 1; even plane: slots n+1..2n <- 2 (o0 + p)), tap offset -1 / 0 / +1 reads from
+    slot 0 / n + 1 / 1 of its axis, MMA row r = (hy, wx) = (r // 8, r % 8) adds hy row pitches and wx slots, depth slice mt adds mt
+    slice pitches.  x: [Di, Hi, Wi, Cin]; w_taps[t]: [Cout, Cin]; offs[t] = (od, oh, ow)."""
+    Di, Hi, Wi, Cin = x.shape
+    Ld, Lh, Lw = out_sp
+    HY, HX, ZS = 2 * BH + 1, 2 * BW + 1, 2 * MT + 1
+    sl = lambda off, n: n + 1 if off == 0 else (1 if off > 0 else 0)
+    out = np.zeros((Ld, Lh, Lw, w_taps[0].shape[0]))
+    for d0, h0, w0 in itertools.product(range(0, Ld, MT), range(0, Lh, BH), range(0, Lw, BW)):
+        halo = np.zeros((ZS, HY, HX, Cin))
+        for z, y in itertools.product(range(ZS), range(HY)):
+            d = 2 * (d0 + z) - 1 if z <= MT else 2 * (d0 + z - (MT + 1))
+            h = 2 * (h0 + y) - 1 if y <= BH else 2 * (h0 + y - (BH + 1))
+            if not (0 <= d < Di and 0 <= h < Hi):
+                continue
+            w_in0 = 2 * w0 - 1
+            for v in range(HX):
+                if 0 <= w_in0 + v < Wi:
+                    slot = (BW + 1) + (v >> 1) if (v & 1) else (v >> 1)
+                    halo[z, y, slot] = x[d, h, w_in0 + v]
+        flat = halo.reshape(ZS * HY * HX, Cin)
+        for t, (od, oh, ow) in enumerate(offs):
+            tapoff = (sl(od, MT) * HY + sl(oh, BH)) * HX + sl(ow, BW)
+            for mt, r in itertools.product(range(MT), range(BH * BW)):
+                hy, wx = r // 8, r % 8
+                d, h, ww = d0 + mt, h0 + hy, w0 + wx
+                if d < Ld and h < Lh and ww < Lw:
+                    out[d, h, ww] += w_taps[t] @ flat[tapoff + mt * HY * HX + hy * HX + wx]
+    return out
+
+
+@pytest.mark.parametrize("in_sp", [(7, 18, 20), (8, 34, 17), (5, 9, 16)])
+def test_deinterleaved_halo_of_the_strided_tile_kernel_conv(in_sp):
+    """3x3x3 stride-2 padding-1 convolution through the emulated S2 addressing == torch."""
+    g = torch.Generator().manual_seed(8)
+    cin, cout = 3, 5
+    x = torch.randn(1, cin, *in_sp, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv3d(x, w, stride=2, padding=1)[0].permute(1, 2, 3, 0).numpy()
+    offs = [(a - 1, b - 1, c - 1) for a, b, c in itertools.product(range(3), repeat=3)]
+    taps = [w[:, :, a, b, c].numpy() for a, b, c in itertools.product(range(3), repeat=3)]
+    out = _emulate_s2_tile_kernel(x[0].permute(1, 2, 3, 0).numpy(), taps, offs, ref.shape[:3])
+    assert np.allclose(out, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_deinterleaved_halo_of_the_strided_tile_kernel_upconv_dgrad():
+    """dgrad of a kernel == stride == 2 transposed convolution = 2x2x2 stride-2 convolution of dy with taps at offsets {0, 1}
+    (ConvPlan.dgrad of a transposed layer) through the emulated S2 addressing == torch autograd."""
+    g = torch.Generator().manual_seed(9)
+    cin, cout, in_sp = 4, 3, (3, 9, 10)
+    x = torch.randn(1, cin, *in_sp, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cin, cout, 2, 2, 2, generator=g, dtype=torch.float64)
+    y = F.conv_transpose3d(x, w, stride=2)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    offs = list(itertools.product(range(2), repeat=3))
+    taps = [w[:, :, a, b, c].numpy() for a, b, c in offs]                  # dx[ci] += W[ci, co, tap] dy[co]
+    out = _emulate_s2_tile_kernel(gy[0].permute(1, 2, 3, 0).numpy(), taps, offs, in_sp)
+    assert np.allclose(out, x.grad[0].permute(1, 2, 3, 0).numpy(), rtol=1e-10, atol=1e-10)

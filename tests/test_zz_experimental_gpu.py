@@ -87,3 +87,64 @@ def test_transposed_conv_wgrad_on_tcgen05(cin, cout, s, shape):
     assert kernels[True] == ["wgrad_tc_s2"] and len(kernels[False]) == (8 if s == 2 else 4)
     assert rel_err(res[True], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[True], res[False]) < 1e-3
+
+
+def _trace_kernels(ops, fn):
+    import csv, tempfile
+    ops.trace_start()
+    out = fn()
+    with tempfile.TemporaryDirectory() as td:
+        ops.trace_dump(os.path.join(td, "t.csv"))
+        rows = list(csv.DictReader(open(os.path.join(td, "t.csv"))))
+    return out, rows
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(32, 64, (2, 12, 34, 36)), (64, 128, (1, 16, 16, 16)), (128, 256, (2, 9, 20, 17)),
+                                           (256, 320, (1, 16, 16, 16))])
+def test_strided_conv_block_forward_on_tcgen05(cin, cout, shape):
+    """nnd_conv_set_gather_strided_tc(1): 3x3x3 stride-2 conv + instance norm + ReLU through the de-interleaved-halo tile kernel
+    (conv_tc.cu, S2 = 1) against the CPU oracle on bf16-exact operands (5e-3) and against the mma.sync kernel (3e-3)."""
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair("instance", cin, cout, 3, 2)
+    g = torch.Generator().manual_seed(63)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    with torch.no_grad():
+        yr = ref(x)
+    xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    res = {}
+    try:
+        for mode in (True, False):
+            ops.set_gather_strided_tc(mode)
+            with torch.no_grad():
+                y, rows = _trace_kernels(ops, lambda: mine(xm))
+            res[mode] = (y.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop"])
+    finally:
+        ops.set_gather_strided_tc(False)
+    assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
+    assert rel_err(res[True][0], yr) < 5e-3
+    assert rel_err(res[True][0], res[False][0]) < 3e-3
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(64, 32, (2, 4, 9, 12)), (128, 64, (1, 5, 8, 8)), (128, 128, (2, 4, 8, 16))])
+def test_upconv_input_gradient_on_tcgen05(cin, cout, shape):
+    """dgrad of kernel == stride == 2 up-convolutions (a 2x2x2 stride-2 gather of dy) through the same kernel."""
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair("instance", cin, cout, None, 2, transposed=True)
+    g = torch.Generator().manual_seed(64)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res = {}
+    try:
+        for mode in (True, False):
+            ops.set_gather_strided_tc(mode)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            _, rows = _trace_kernels(ops, lambda: mine(xm).backward(gy.cuda().to(torch.bfloat16)))
+            res[mode] = (xm.grad.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop" and int(r["T"]) == 8])
+    finally:
+        ops.set_gather_strided_tc(False)
+    assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
+    assert rel_err(res[True][0], xr.grad) < 5e-3
+    assert rel_err(res[True][0], res[False][0]) < 3e-3
