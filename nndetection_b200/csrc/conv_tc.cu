@@ -95,7 +95,8 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   if (S2) {
     // slot of output 0 on an axis with n outputs per tile: odd plane first (n + 1 slots), then the even plane
     auto sl = [](int off, int n) { return off == 0 ? n + 1 : (off > 0 ? 1 : 0); };
-    if (tid < T) s_tapoff[tid] = ((sl(g.off_d[tid], MT) * HY + sl(g.off_h[tid], BH)) * HX + sl(g.off_w[tid], BW)) * 16;
+    // the depth axis may be unstrided (first stride (1, 2, 2) of anisotropic plans): ordinary halo slots d0 - 1 + z there
+    if (tid < T) s_tapoff[tid] = (((g.sd == 2 ? sl(g.off_d[tid], MT) : g.off_d[tid] + 1) * HY + sl(g.off_h[tid], BH)) * HX + sl(g.off_w[tid], BW)) * 16;
   } else {
     if (tid < T) s_tapoff[tid] = (((g.off_d[tid] + 1) * HY + (g.off_h[tid] + 1)) * HX + (g.off_w[tid] + 1)) * 16;
   }
@@ -168,9 +169,9 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
         }
         } else {
           // slot -> input position: odd plane slot p -> 2 (o0 + p) - 1, even plane slot n + 1 + p -> 2 (o0 + p)
-          const int d = z <= MT ? 2 * (d0 + z) - 1 : 2 * (d0 + z - (MT + 1));
+          const int d = g.sd == 2 ? (z <= MT ? 2 * (d0 + z) - 1 : 2 * (d0 + z - (MT + 1))) : d0 - 1 + z;
           const int h = y <= BH ? 2 * (h0 + y) - 1 : 2 * (h0 + y - (BH + 1));
-          const bool row_ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
+          const bool row_ok = (g.sd == 2 || z < MT + 2) && (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
           const int w_in0 = 2 * w0 - 1;
           const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + w_in0) * g.Cin + gidx * 8;
           const unsigned dst0 = a_base + rr * (HX * 16);
@@ -424,10 +425,10 @@ int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep) {
 
 // Stride-2 gathers (S2 variant): 3x3x3 stride-2 convolutions and the 2x2x2 stride-2 convolution behind an up-convolution's dgrad.
 int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep) {
-  if (g.sd != 2 || g.sh != 2 || g.sw != 2) return 0;
+  if (g.sd < 1 || g.sd > 2 || g.sh != 2 || g.sw != 2) return 0;
   if (g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
   if (g.Ld != g.Do || g.Lh != g.Ho || g.Lw != g.Wo) return 0;
-  if (g.T < 8 || g.Cin % 16) return 0;
+  if (g.T < 4 || g.Cin % 16) return 0;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
   if (ep.out_fp32 || ep.Cout % 32 || ep.CoutPad != ep.Cout) return 0;

@@ -201,7 +201,7 @@ def test_transposed_plan_exposes_the_swapped_weight_gradient_geometry():
     assert taps == [(a, b, c, (a * 2 + b) * 2 + c) for a, b, c in itertools.product(range(2), repeat=3)]
 
 
-def _emulate_s2_tile_kernel(x, w_taps, offs, out_sp, MT=2, BH=16, BW=8):
+def _emulate_s2_tile_kernel(x, w_taps, offs, out_sp, MT=2, BH=16, BW=8, sd=2):
     """Index arithmetic of conv_tc.cu, S2 = 1 in numpy: per tile (MT x 16 x 8 outputs) the halo is staged de-interleaved per axis
     (odd plane: slots 0..n <- positions 2 (o0 + p) - 1; even plane: slots n+1..2n <- 2 (o0 + p)), tap offset -1 / 0 / +1 reads from
     slot 0 / n + 1 / 1 of its axis, MMA row r = (hy, wx) = (r // 8, r % 8) adds hy row pitches and wx slots, depth slice mt adds mt
@@ -214,9 +214,9 @@ def _emulate_s2_tile_kernel(x, w_taps, offs, out_sp, MT=2, BH=16, BW=8):
     for d0, h0, w0 in itertools.product(range(0, Ld, MT), range(0, Lh, BH), range(0, Lw, BW)):
         halo = np.zeros((ZS, HY, HX, Cin))
         for z, y in itertools.product(range(ZS), range(HY)):
-            d = 2 * (d0 + z) - 1 if z <= MT else 2 * (d0 + z - (MT + 1))
+            d = (2 * (d0 + z) - 1 if z <= MT else 2 * (d0 + z - (MT + 1))) if sd == 2 else d0 - 1 + z
             h = 2 * (h0 + y) - 1 if y <= BH else 2 * (h0 + y - (BH + 1))
-            if not (0 <= d < Di and 0 <= h < Hi):
+            if not ((sd == 2 or z < MT + 2) and 0 <= d < Di and 0 <= h < Hi):
                 continue
             w_in0 = 2 * w0 - 1
             for v in range(HX):
@@ -225,7 +225,7 @@ def _emulate_s2_tile_kernel(x, w_taps, offs, out_sp, MT=2, BH=16, BW=8):
                     halo[z, y, slot] = x[d, h, w_in0 + v]
         flat = halo.reshape(ZS * HY * HX, Cin)
         for t, (od, oh, ow) in enumerate(offs):
-            tapoff = (sl(od, MT) * HY + sl(oh, BH)) * HX + sl(ow, BW)
+            tapoff = ((sl(od, MT) if sd == 2 else od + 1) * HY + sl(oh, BH)) * HX + sl(ow, BW)
             for mt, r in itertools.product(range(MT), range(BH * BW)):
                 hy, wx = r // 8, r % 8
                 d, h, ww = d0 + mt, h0 + hy, w0 + wx
@@ -262,3 +262,16 @@ def test_deinterleaved_halo_of_the_strided_tile_kernel_upconv_dgrad():
     taps = [w[:, :, a, b, c].numpy() for a, b, c in offs]                  # dx[ci] += W[ci, co, tap] dy[co]
     out = _emulate_s2_tile_kernel(gy[0].permute(1, 2, 3, 0).numpy(), taps, offs, in_sp)
     assert np.allclose(out, x.grad[0].permute(1, 2, 3, 0).numpy(), rtol=1e-10, atol=1e-10)
+
+
+def test_deinterleaved_halo_with_an_unstrided_depth_axis():
+    """First stride (1, 2, 2) of anisotropic plans (LIDC-shaped config): ordinary halo slots along d, de-interleaved h / w."""
+    g = torch.Generator().manual_seed(10)
+    cin, cout, in_sp = 3, 4, (5, 18, 20)
+    x = torch.randn(1, cin, *in_sp, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv3d(x, w, stride=(1, 2, 2), padding=1)[0].permute(1, 2, 3, 0).numpy()
+    offs = [(a - 1, b - 1, c - 1) for a, b, c in itertools.product(range(3), repeat=3)]
+    taps = [w[:, :, a, b, c].numpy() for a, b, c in itertools.product(range(3), repeat=3)]
+    out = _emulate_s2_tile_kernel(x[0].permute(1, 2, 3, 0).numpy(), taps, offs, ref.shape[:3], sd=1)
+    assert np.allclose(out, ref, rtol=1e-10, atol=1e-10)
