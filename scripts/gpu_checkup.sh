@@ -30,3 +30,10 @@ with open("gpurun_out/layers_summary.txt", "w") as f:
         f.write(f"{v[0]:7.3f} {100 * v[0] / tot:6.2f} {v[2]:3d} {v[1] / max(v[0], 1e-9):8.1f}  {k[0]:12s} {k[1]:14s} {k[2]:>3s}->{k[3]:<4s} {k[4]:11s} {k[5]:6s} {k[6]}\n")
 PY
 tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
+# single-layer timings of the strided forms, default kernels vs the opt-in tcgen05 ones
+for args in "32 64 128 4" "64 128 64 4" "128 256 32 4"; do
+  for m in fprop wgrad; do
+    NND_STRIDE=2 timeout 120 python scripts/profile_conv.py $args $m 2>&1 | tail -1
+    NND_STRIDE=2 NND_S2=1 timeout 120 python scripts/profile_conv.py $args $m 2>&1 | tail -1
+  done
+done | tee gpurun_out/strided_layers.txt

@@ -1,4 +1,7 @@
-"""Run single conv layers in isolation (for `ncu --set full -k regex:conv_`): python scripts/profile_conv.py [cin cout size batch]"""
+"""Run single conv layers in isolation (for `ncu --set full -k regex:conv_`):
+    python scripts/profile_conv.py [cin cout size batch [fprop|wgrad [wgrad_tc_mode]]]
+env: NND_STREAM=mode,issuers  NND_TC_RING=n  NND_STRIDE=2 (3x3x3 stride-2 layer, `size` = input size)  NND_S2=1 (opt-in tcgen05 kernels
+for the strided forms: conv_tc S2 / conv_wgrad_tc SW=2)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,14 +21,20 @@ if os.environ.get("NND_TC_RING"):
     from nndetection_b200 import _lib as L2
     from ctypes import c_int as _ci
     L2.lib().nnd_conv_set_tc_ring(_ci(int(os.environ["NND_TC_RING"])))
+stride = int(os.environ.get("NND_STRIDE", "1"))
+if os.environ.get("NND_S2"):
+    ops.set_gather_strided_tc(True)
+    ops.set_wgrad_strided_tc(True)
 dev = torch.device("cuda")
-layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
+layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=stride, padding=1).to(dev)
 x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
 plan = layer.plan(bs, (size,) * 3)
 wp, wb = layer.packed()
 y = ops.empty_cl(bs, cout, plan.out_sp, device=dev)
 st = torch.zeros((2, bs, cout), dtype=torch.float32, device=dev)
 dw = torch.zeros_like(layer.conv.weight)
+if mode != "fprop":
+    y.normal_()                      # stands in for dy
 def run():
     if mode == "fprop":
         return ops.conv_gather(x, wp, plan.fprop[0], y, cout, cout, stat_sum=st[0], stat_sq=st[1])
@@ -39,5 +48,5 @@ for _ in range(5):
     run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-fl = 2.0 * 27 * cin * cout * bs * size ** 3
-print(f"{mode} {cin}->{cout} @{size}^3 x{bs} stream={os.environ.get('NND_STREAM', 'default')}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  (kernel code {run()})")
+fl = 2.0 * 27 * cin * cout * bs * plan.out_sp[0] * plan.out_sp[1] * plan.out_sp[2]
+print(f"{mode} {cin}->{cout} @{size}^3 x{bs} stride={stride} s2={os.environ.get('NND_S2', '0')} stream={os.environ.get('NND_STREAM', 'default')}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  (kernel code {run()})")
