@@ -6,3 +6,4 @@ from .ensembler import (BoxEnsemblerSelective, batched_nms_ensemble, batched_nms
 from .predictor import SlidingWindowPredictor, create_grid, get_tta_dims, mirror_boxes  # noqa: F401
 from .helper import (get_loader_fn, get_predictor, load_all_models, load_final_model, predict_dir,  # noqa: F401
                      save_checkpoint)
+from .sweeper import BoxSweeper  # noqa: F401

@@ -141,6 +141,10 @@ class BoxEnsemblerSelective:
         return cls(properties=_properties, parameters=_parameters, box_key=box_key, score_key=score_key, label_key=label_key,
                    data_key=data_key, device=device, **kwargs)
 
+    def update_parameters(self, **parameters) -> None:
+        """ensembler/base.py:153-160 (the sweep overwrites one parameter at a time)."""
+        self.parameters.update(parameters)
+
     def add_model(self, name: Optional[Hashable] = None, model_weight: Optional[float] = None) -> Hashable:
         """ensembler/base.py:90-113."""
         if name is None:

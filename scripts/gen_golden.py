@@ -466,6 +466,71 @@ def gen_helper():
     save("helper", **out)
 
 
+# ------------------------------------------------------------------------------------------ post-processing sweep
+def gen_sweeper():
+    """`BoxSweeper` (nndet/inference/sweeper.py:78-219) EXECUTED from its file on saved ensembler states, against this package's
+    mirror: identical determined parameters and identical score per swept value, (a) with the reference's real `BoxEvaluator` (COCO mAP;
+    matplotlib stubbed) and (b) with the small stand-in evaluator the committed test can run; (b) goes into tests/golden/sweeper.npz."""
+    import importlib, importlib.util, json, tempfile, types
+    root = ref_import.REF_ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import tutil
+    from nndetection_b200.inference.sweeper import BoxSweeper
+
+    def load(modname, rel):
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(root, rel))
+        m = importlib.util.module_from_spec(spec); sys.modules[modname] = m; spec.loader.exec_module(m); return m
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.ticker"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib.ticker"].FuncFormatter = object
+    sys.modules["matplotlib.pyplot"].Figure = sys.modules["matplotlib.pyplot"].Axes = object      # only used in annotations
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if "nndet.io" not in sys.modules or not hasattr(sys.modules["nndet.io"], "__path__"):
+        pkg = types.ModuleType("nndet.io"); pkg.__path__ = []; sys.modules["nndet.io"] = pkg
+    load("nndet.io.paths", "nndet/io/paths.py")
+    load("nndet.io.load", "nndet/io/load.py")
+    from nndet.evaluator.registry import BoxEvaluator
+    rsw = load("ref_sweeper", "nndet/inference/sweeper.py")
+    os.environ["det_verbose"] = "0"
+
+    ens_cls = tutil.oracle_ensembler_cls()
+    classes = ["class0", "class1"]
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        pred, gt = os.path.join(td, "pred"), os.path.join(td, "gt")
+        tutil.write_sweep_cases(pred, gt)
+        for tag, ev, metric in (("coco", BoxEvaluator, "mAP_IoU_0.10_0.50_0.05_MaxDet_100"), ("standin", tutil.StandInEvaluator, "stand_in")):
+            ref = rsw.BoxSweeper(classes=classes, pred_dir=pred, gt_dir=gt, target_metric=metric, ensembler_cls=ens_cls,
+                                 save_dir=os.path.join(td, f"ref_{tag}"))
+            ref.evaluator_cls = ev
+            state_ref = ref.run_postprocessing_sweep()
+            mine = BoxSweeper(classes, pred, gt, metric, ens_cls, save_dir=os.path.join(td, f"mine_{tag}"), evaluator_cls=ev, device="cpu")
+            state_mine = mine.run_postprocessing_sweep()
+            assert list(state_ref.keys()) == list(state_mine.keys())
+            for k in state_ref:
+                assert state_ref[k] == state_mine[k] or state_ref[k] is state_mine[k], (tag, k, state_ref[k], state_mine[k])
+            for f in sorted(os.listdir(os.path.join(td, f"ref_{tag}"))):
+                a = json.load(open(os.path.join(td, f"ref_{tag}", f))); b = json.load(open(os.path.join(td, f"mine_{tag}", f)))
+                assert list(a.keys()) == list(b.keys()), f
+                for k in a:
+                    if k.startswith("best_"):
+                        assert a[k] == b[k], (tag, f, k)
+                    else:
+                        assert a[k]["scores"] == b[k]["scores"] and a[k]["overwrite"] == b[k]["overwrite"], (tag, f, k)
+                if tag == "standin":
+                    vals = [float(eval(v["scores"], {"np": np, "nan": float("nan")})["stand_in"]) for k, v in a.items() if not k.startswith("best_")]
+                    assert len(set(vals)) == len(vals) or np.argmax(vals) == 0 or sorted(vals)[-1] > sorted(vals)[-2], f"tie at the top in {f}"
+                    out["scores_" + f[len("sweep_"):-len(".json")]] = np.asarray(vals)
+            print(f"  {tag}: determined", {k: (v.__name__ if callable(v) else float(v)) for k, v in state_ref.items()
+                                           if k in ("model_iou", "model_nms_fn", "ensemble_iou", "model_score_thresh", "remove_small_boxes")})
+            if tag == "standin":
+                for k in ("model_iou", "ensemble_iou", "model_score_thresh", "remove_small_boxes"):
+                    out["state_" + k] = np.float64(state_ref[k])
+                out["state_model_nms_fn"] = np.asarray(state_ref["model_nms_fn"].__name__)
+    save("sweeper", **out)
+
+
 # ------------------------------------------------------------------------------------------ learning-rate schedule
 def gen_lr():
     """LinearWarmupPolyLR (nndet/training/learning_rate.py:126-183) executed: the lr the optimizer holds at every step."""
@@ -755,7 +820,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "helper", "lr", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "helper", "sweeper", "lr", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

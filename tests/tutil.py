@@ -135,3 +135,101 @@ class FakeDetector:
             out["pred_scores"].append((flat[idx] * 0.9 + 0.1 * salt).clone())
             out["pred_labels"].append(((z + y + x) % 2).long())
         return out
+
+
+# ------------------------------------------------------------------ sweep fixtures (tests/test_sweeper_cpu.py, scripts/gen_golden.py sweeper)
+def o_weighted_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+    from oracle import box_oracle as bo
+    keep = bo.batched_nms(boxes, scores * weights, labels, iou_thresh, cuda_semantics=False)
+    return boxes[keep], scores[keep], labels[keep], torch.ones_like(weights)[keep]
+
+
+def o_nms_model(boxes, scores, labels, weights, iou_thresh, *a, **k):
+    from oracle import box_oracle as bo
+    keep = bo.batched_nms(boxes, scores, labels, iou_thresh, cuda_semantics=False)
+    return boxes[keep], scores[keep], labels[keep], weights[keep]
+
+
+def o_wbc_ensemble(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh, *a, **k):
+    from oracle import box_oracle as bo
+    return bo.batched_wbc(boxes, scores, labels, weights, iou_thresh, n_exp_preds, score_thresh)
+
+
+def oracle_ensembler_cls():
+    """`BoxEnsemblerSelective` whose default / sweep parameters name the oracle's CPU NMS / WBC instead of the device kernels."""
+    from nndetection_b200.inference.ensembler import BoxEnsemblerSelective, batched_nms_model, batched_weighted_nms_model
+
+    class OracleEnsembler(BoxEnsemblerSelective):
+        @classmethod
+        def get_default_parameters(cls):
+            d = super().get_default_parameters()
+            d.update(model_nms_fn=o_weighted_nms_model, ensemble_nms_fn=o_wbc_ensemble)
+            return d
+
+        @classmethod
+        def sweep_parameters(cls):
+            _, sweep = BoxEnsemblerSelective.sweep_parameters()
+            swap = {batched_weighted_nms_model: o_weighted_nms_model, batched_nms_model: o_nms_model}
+            sweep["model_nms_fn"] = [swap[f] for f in sweep["model_nms_fn"]]
+            return cls.get_default_parameters(), sweep
+    return OracleEnsembler
+
+
+class StandInEvaluator:
+    """Evaluator protocol of nndet/evaluator/det.py:BoxEvaluator (create / run_online_evaluation / finish_online_evaluation) with a
+    small deterministic metric: per ground-truth box the best score * IoU among same-class predictions, averaged over all boxes, minus
+    a 0.0003 penalty per prediction per case -- sensitive to every swept parameter, no ties on the fixtures."""
+
+    @classmethod
+    def create(cls, classes, fast=True, verbose=False, save_dir=None):
+        return cls()
+
+    def __init__(self):
+        self.hits, self.n_gt, self.n_pred, self.n_cases = 0.0, 0, 0, 0
+
+    def run_online_evaluation(self, pred_boxes, pred_classes, pred_scores, gt_boxes, gt_classes, gt_ignore=None):
+        from oracle import box_oracle as bo
+        for pb, pc, ps, gb, gc in zip(pred_boxes, pred_classes, pred_scores, gt_boxes, gt_classes):
+            self.n_cases += 1
+            self.n_pred += len(pb)
+            self.n_gt += len(gb)
+            if len(pb) == 0 or len(gb) == 0:
+                continue
+            iou = bo.box_iou(torch.as_tensor(np.asarray(gb, dtype=np.float32)), torch.as_tensor(np.asarray(pb, dtype=np.float32))).numpy()
+            same = np.asarray(gc).reshape(-1, 1) == np.asarray(pc).reshape(1, -1)
+            self.hits += float((iou * same * np.asarray(ps, dtype=np.float64).reshape(1, -1)).max(axis=1).sum())
+
+    def finish_online_evaluation(self):
+        return {"stand_in": self.hits / max(self.n_gt, 1) - 0.0003 * self.n_pred / max(self.n_cases, 1)}, None
+
+
+def write_sweep_cases(pred_dir, gt_dir, n_cases=3):
+    """Ensembler states (`<case>_boxes.pt`) of synthetic tile predictions + ground truth derived from each case's own strongest,
+    mutually distant predictions (so that good post-processing parameters exist)."""
+    import os
+    ens_cls = oracle_ensembler_cls()
+    os.makedirs(pred_dir, exist_ok=True); os.makedirs(gt_dir, exist_ok=True)
+    for ci in range(n_cases):
+        models, shape = synth_tile_predictions(100 + ci)
+        # second "model" (TTA pass) = jittered copy of the first one's detections + its own: overlapping duplicates inside a pass
+        # (tiles overlap) and across passes, so the NMS / WBC thresholds matter
+        gj = torch.Generator().manual_seed(900 + ci)
+        for (res1, _), (res2, _) in zip(models[0], models[1]):
+            for j in range(len(res1["pred_boxes"])):
+                b1, s1, l1 = res1["pred_boxes"][j], res1["pred_scores"][j], res1["pred_labels"][j]
+                jit = b1 + (torch.rand(b1.shape, generator=gj) - 0.5) * 1.5
+                res2["pred_boxes"][j] = torch.cat([res2["pred_boxes"][j], jit])
+                res2["pred_scores"][j] = torch.cat([res2["pred_scores"][j], (s1 * (0.6 + 0.4 * torch.rand(s1.shape, generator=gj))).clamp(0.001, 0.999)])
+                res2["pred_labels"][j] = torch.cat([res2["pred_labels"][j], l1])
+        ens = ens_cls.from_case({"data": torch.zeros(1, *shape)}, properties={}, parameters=None)
+        for mi, batches in enumerate(models):
+            ens.add_model(name=f"model0_t{mi}", model_weight=1.0 if mi == 0 else 0.7)
+            for res, batch in batches:
+                ens.process_batch(result=res, batch=batch)
+        out = ens.get_case_result()
+        b, l = out["pred_boxes"].numpy(), out["pred_labels"].numpy()
+        pick = list(range(0, min(len(b), 24), 2))                  # every second of the 24 best consolidated detections
+        rs = np.random.RandomState(ci)
+        gtb = b[pick] + rs.uniform(-1.0, 1.0, size=(len(pick), 6)).astype(np.float32)
+        np.savez(os.path.join(gt_dir, f"case_{ci}_boxes_gt.npz"), boxes=gtb, classes=l[pick].astype(np.int64))
+        ens.save_state(pred_dir, f"case_{ci}")
