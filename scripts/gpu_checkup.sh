@@ -37,3 +37,5 @@ for args in "32 64 128 4" "64 128 64 4" "128 256 32 4"; do
     NND_STRIDE=2 NND_S2=1 timeout 120 python scripts/profile_conv.py $args $m 2>&1 | tail -1
   done
 done | tee gpurun_out/strided_layers.txt
+# BASELINE config 4 through the predictor + ensembler (one 288^3 case, 160^3 patches, 8 mirror passes)
+timeout 300 python scripts/bench_inference.py > gpurun_out/bench_inference.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_inference.json
