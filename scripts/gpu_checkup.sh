@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call that re-establishes the ground truth on a fresh B200 box (run from the repo root):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_checkup.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash scripts/gpu_checkup.sh'      (typically ~15 min)
 # Outputs land in gpurun_out/: pytest log (incl. XPASS/xfail of the tests written without a GPU), the default bench line (with the
 # stock-PyTorch gpu_baseline and the CPU baseline), the per-launch convolution trace of one train step (layer geometry -> kernel -> ms),
 # and the ncu launch list of the same step.  Every stage has its own timeout so a hang cannot take the box down with it.
