@@ -62,6 +62,8 @@ def poly_lr(step: int, initial_lr: float, warm_iterations: int, warm_lr: float, 
     if step < warm_iterations:
         return warm_lr + (initial_lr - warm_lr) * (float(step + 1) / float(warm_iterations))
     poly_iterations = num_iterations - warm_iterations
+    if poly_iterations <= 0:            # degenerate schedule (the reference would divide by zero): stay at the plateau
+        return initial_lr
     it = step + 1 - warm_iterations
     if it >= poly_iterations:
         it = poly_iterations - 1
