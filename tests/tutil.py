@@ -233,3 +233,21 @@ def write_sweep_cases(pred_dir, gt_dir, n_cases=3):
         gtb = b[pick] + rs.uniform(-1.0, 1.0, size=(len(pick), 6)).astype(np.float32)
         np.savez(os.path.join(gt_dir, f"case_{ci}_boxes_gt.npz"), boxes=gtb, classes=l[pick].astype(np.int64))
         ens.save_state(pred_dir, f"case_{ci}")
+
+
+def toy_learning_batch(patch, bs, seed):
+    """The reference's toy data (scripts/generate_example.py:49-98) at patch size: uniform noise, one cuboid of side U[6, 12) per image
+    with +0.4 intensity = the object (class 0); seg = the cuboid."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(bs, 1, *patch, generator=g)
+    tb, tc = [], []
+    seg = torch.zeros(bs, *patch)
+    for i in range(bs):
+        lo = [int(torch.randint(1, patch[ax] - 13, (1,), generator=g)) for ax in range(3)]
+        sd = [int(torch.randint(6, 12, (1,), generator=g)) for _ in range(3)]
+        sl = tuple(slice(l, l + s) for l, s in zip(lo, sd))
+        images[i, 0][sl] += 0.4
+        seg[i][sl] = 1
+        tb.append(torch.tensor([[lo[0] + 0.318, lo[1] + 0.328, lo[0] + sd[0] - 0.359, lo[1] + sd[1] - 0.349, lo[2] + 0.338, lo[2] + sd[2] - 0.339]]))
+        tc.append(torch.zeros(1, dtype=torch.int64))
+    return images, dict(target_boxes=tb, target_classes=tc, target_seg=seg)
