@@ -81,6 +81,23 @@ def shifted_crop(dshape: Sequence[int], crop: Sequence[slice]) -> Tuple[List[int
     return [int(s.start) for s in out], out
 
 
+def padded_crop_symmetric(data: Tensor, crop: Sequence[slice]) -> Tuple[Tensor, List[int], List[slice]]:
+    """`_padded_crop(mode="symmetric")`, patching.py:396-452 = `np.pad(data[clipped crop], mode="symmetric")`, as index gathers on
+    the device: position p of an axis clipped to [lb, ub) (n = ub - lb) reads lb + m if m < n else lb + 2n - 1 - m with
+    m = (p - lb) mod 2n (edge value repeated, reflections continue periodically).  Returns (tile, origin = crop starts, crop)."""
+    out = data
+    nd = data.dim() - len(crop)
+    for ax, (c, dim) in enumerate(zip(crop, data.shape[nd:])):
+        lb, ub = max(c.start, 0), min(c.stop, dim)
+        n = ub - lb
+        if n <= 0:
+            raise RuntimeError("crop lies completely outside of the data")
+        m = (torch.arange(c.start, c.stop, device=data.device) - lb) % (2 * n)
+        idx = lb + torch.where(m < n, m, 2 * n - 1 - m)
+        out = out.index_select(nd + ax, idx)
+    return out, [int(c.start) for c in crop], list(crop)
+
+
 # ------------------------------------------------------------------ mirror TTA (nndet/io/transforms/spatial.py, inference/transforms.py)
 def mirror(data: Tensor, dims: Sequence[int]) -> Tensor:
     """spatial.py:87-99: flip the given spatial dims of [N, C, spatial...]."""
@@ -134,15 +151,20 @@ class SlidingWindowPredictor:
         self.ensembler = None
 
     def tile_case(self, case: Dict) -> List[Dict]:
-        """predictor.py:192-235: tiles as VIEWS of the (device-resident) case + their origin / crop.  A patch larger than the
-        case in some axis (the reference's np.pad "symmetric" fallback, :223-228) is not supported."""
+        """predictor.py:192-235: tiles as VIEWS of the (device-resident) case + their origin / crop.  When the patch is larger than
+        the case in some axis the crop is taken with symmetric padding instead (the reference's fallback, :223-228): a copy, origin =
+        the (possibly negative) crop start."""
         data = case[self.data_key]
         dshape = tuple(data.shape[1:])
         overlap = [int(c * self.overlap) for c in self.crop_size]
         tiles = []
         for crop in create_grid(cshape=self.crop_size, dshape=dshape, overlap=overlap, mode=self.grid_mode):
-            origin, sc = shifted_crop(dshape, crop)
-            tiles.append({self.data_key: data[(slice(None), *sc)], "tile_origin": origin, "crop": sc})
+            try:
+                origin, sc = shifted_crop(dshape, crop)
+                tile = data[(slice(None), *sc)]
+            except RuntimeError:
+                tile, origin, sc = padded_crop_symmetric(data, crop)
+            tiles.append({self.data_key: tile, "tile_origin": origin, "crop": sc})
         return tiles
 
     @torch.no_grad()

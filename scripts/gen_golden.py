@@ -324,6 +324,12 @@ def gen_predictor():
     for dims in [(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)]:
         r = rspat.Mirror(keys=["pred_seg"], box_keys=["pred_boxes"], dims=dims)(pred_seg=torch.zeros(1, 2, 32, 40, 24), pred_boxes=[bx])
         assert torch.equal(r["pred_boxes"][0], mp.mirror_boxes(bx, dims, (32, 40, 24)))
+    # ---- patch larger than the case: the predictor's fallback save_get_crop(mode="symmetric") (predictor.py:223-228)
+    small = torch.rand(2, 5, 40, 7, generator=g)
+    for crop in rpatch.create_grid(cshape=(16, 32, 16), dshape=(5, 40, 7), overlap=[8, 16, 8], mode="symmetric"):
+        r_tile, r_origin, r_crop = rpatch.save_get_crop(small.numpy(), crop, mode="symmetric")
+        m_tile, m_origin, m_crop = mp.padded_crop_symmetric(small, crop)
+        assert np.array_equal(r_tile, m_tile.numpy()) and list(r_origin) == m_origin and list(r_crop) == m_crop
     # ---- whole loop: case -> tiles -> 8 mirror TTAs -> ensembler
     g = torch.Generator().manual_seed(17)
     case = {"data": torch.rand(1, 40, 56, 48, generator=g).numpy()}

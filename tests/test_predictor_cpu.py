@@ -89,3 +89,22 @@ def test_tile_sharding_over_two_ranks_gives_the_single_process_result():
         assert p.exitcode == 0
     assert np.array_equal(res["pred_boxes"], g["case_boxes"]) and np.array_equal(res["pred_scores"], g["case_scores"])
     assert np.array_equal(res["pred_labels"], g["case_labels"])
+
+
+def test_patch_larger_than_the_case_falls_back_to_symmetric_padding():
+    """predictor.py:223-228 / patching.py:396-452: `np.pad(mode="symmetric")` of the clipped crop, origin = crop start (negative);
+    also with pads wider than the data (several reflections)."""
+    from nndetection_b200.inference.predictor import SlidingWindowPredictor, create_grid, padded_crop_symmetric
+    g = torch.Generator().manual_seed(4)
+    data = torch.rand(2, 5, 40, 7, generator=g)
+    for crop in [(slice(-3, 9), slice(4, 36), slice(-2, 10)), (slice(-14, 18), slice(-1, 31), slice(-13, 19)), (slice(1, 4), slice(0, 40), slice(5, 9))]:
+        tile, origin, c = padded_crop_symmetric(data, crop)
+        clipped = tuple(slice(max(s.start, 0), min(s.stop, d)) for s, d in zip(crop, data.shape[1:]))
+        pads = [(0, 0)] + [(max(-s.start, 0), max(s.stop - d, 0)) for s, d in zip(crop, data.shape[1:])]
+        ref = np.pad(data.numpy()[(slice(None), *clipped)], pads, mode="symmetric")
+        assert np.array_equal(tile.numpy(), ref) and origin == [s.start for s in crop] and list(c) == list(crop)
+    pred = SlidingWindowPredictor(lambda c, properties=None: None, [], (16, 32, 16), 0.5, 8, 4, device="cpu")
+    tiles = pred.tile_case({"data": data})
+    crops = create_grid((16, 32, 16), (5, 40, 7), [8, 16, 8], mode="symmetric")
+    assert len(tiles) == len(crops) and all(t["data"].shape == (2, 16, 32, 16) for t in tiles)
+    assert [t["tile_origin"] for t in tiles] == [[s.start for s in c] for c in crops]
