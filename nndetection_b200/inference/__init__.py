@@ -5,5 +5,5 @@ from .ensembler import (BoxEnsemblerSelective, batched_nms_ensemble, batched_nms
                         batched_weighted_nms_model, wbc_nms_no_label_ensemble)
 from .predictor import SlidingWindowPredictor, create_grid, get_tta_dims, mirror_boxes  # noqa: F401
 from .helper import (get_loader_fn, get_predictor, load_all_models, load_final_model, predict_dir,  # noqa: F401
-                     save_checkpoint)
+                     save_checkpoint, sweep)
 from .sweeper import BoxSweeper  # noqa: F401

@@ -116,9 +116,9 @@ def get_loader_fn(mode: str, **kwargs) -> Callable:
 
 # ------------------------------------------------------------------ predictor factory (nndet/ptmodule/retinaunet/base.py:697-745)
 def get_predictor(plan: Dict, models: Sequence[Any], num_tta_transforms: Optional[int] = None, do_seg: bool = False,
-                  **kwargs) -> SlidingWindowPredictor:
-    """Patch size and batch size from the plan, the box ensembler parameterised by the plan's `inference_plan` (the sweep's result),
-    8 mirror passes for 3-D networks."""
+                  ensembler_cls: Callable = BoxEnsemblerSelective, **kwargs) -> SlidingWindowPredictor:
+    """Patch size and batch size from the plan, the box ensembler (`get_ensembler_cls(key="boxes", dim=3)`, base.py:677-695)
+    parameterised by the plan's `inference_plan` (the sweep's result), 8 mirror passes for 3-D networks."""
     if plan.get("network_dim", 3) != 3:
         raise NotImplementedError("2-D networks are outside this path (the reference raises here too, base.py:742-743)")
     if do_seg:
@@ -127,7 +127,7 @@ def get_predictor(plan: Dict, models: Sequence[Any], num_tta_transforms: Optiona
     if num_tta_transforms is None:
         num_tta_transforms = 8
     return SlidingWindowPredictor(
-        ensembler_fn=partial(BoxEnsemblerSelective.from_case, parameters=inference_plan),
+        ensembler_fn=partial(ensembler_cls.from_case, parameters=inference_plan),
         models=models, crop_size=plan["patch_size"], num_tta_transforms=num_tta_transforms, batch_size=plan["batch_size"], **kwargs)
 
 
@@ -166,3 +166,27 @@ def predict_dir(source_dir: Pathlike, target_dir: Pathlike, cfg: dict, plan: dic
             for key, item in to_numpy(result).items():
                 save_pickle(item, target_dir / f"{case_id}_{key}.pkl")
     return predictor
+
+
+# ------------------------------------------------------------------ nndet/ptmodule/retinaunet/base.py:747-815
+def sweep(cfg: dict, plan: dict, save_dir: Pathlike, train_data_dir: Pathlike, case_ids: Sequence[str], run_prediction: bool = True,
+          sweep_ckpt: str = "last", eval_score_key: str = "mAP_IoU_0.10_0.50_0.05_MaxDet_100", ensembler_cls: Callable = BoxEnsemblerSelective,
+          evaluator_cls: Optional[Callable] = None, sweep_device: str = "cuda", **kwargs) -> Dict[str, Any]:
+    """`RetinaUNetModule.sweep`: predict the validation cases with the default post-processing and keep the ensembler states
+    (`<save_dir>/sweep_predictions`), then search the post-processing parameters on them (`<save_dir>/sweep/sweep_<param>.json`).
+    Returns the inference plan (to be stored as `plan["inference_plan"]`).  Ground truth: `<preprocessed>/labelsTr/<case>_boxes_gt.npz`
+    next to `train_data_dir`, classes from `cfg["data"]["labels"]`, like the reference.  `kwargs` go to `predict_dir`."""
+    from .sweeper import BoxSweeper
+    save_dir, train_data_dir = Path(save_dir), Path(train_data_dir)
+    processed_eval_labels = train_data_dir.parent / "labelsTr"
+    (save_dir / "sweep").mkdir(parents=True, exist_ok=True)
+    prediction_dir = save_dir / "sweep_predictions"
+    prediction_dir.mkdir(parents=True, exist_ok=True)
+    if run_prediction:
+        predict_dir(source_dir=train_data_dir, target_dir=prediction_dir, cfg=cfg, plan=plan, source_models=save_dir, num_models=1,
+                    num_tta_transforms=None, case_ids=case_ids, save_state=True, model_fn=get_loader_fn(mode=sweep_ckpt),
+                    ensembler_cls=ensembler_cls, **kwargs)
+    sweeper = BoxSweeper(classes=[item for _, item in cfg["data"]["labels"].items()], pred_dir=prediction_dir, gt_dir=processed_eval_labels,
+                         target_metric=eval_score_key, ensembler_cls=ensembler_cls, save_dir=save_dir / "sweep",
+                         evaluator_cls=evaluator_cls, device=sweep_device)
+    return sweeper.run_postprocessing_sweep()
