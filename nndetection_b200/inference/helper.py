@@ -155,14 +155,13 @@ def predict_dir(source_dir: Pathlike, target_dir: Pathlike, cfg: dict, plan: dic
             case = np.load(str(path)[:-4] + ".npy", allow_pickle=True)
         properties = load_pickle(path.parent / f"{case_id}.pkl")
         properties["transpose_backward"] = plan["transpose_backward"]
-        result = predictor.predict_case({"data": case}, properties, restore=restore)
-        if result is None:                       # tile sharding: only rank 0 holds the case result
-            continue
-        target_dir.mkdir(parents=True, exist_ok=True)
-        if save_state:                           # predictor.py:180-185
-            predictor.ensembler.save_state(target_dir, name=case_id)
-            save_pickle(properties, target_dir / f"{case_id}_properties.pkl")
+        if save_state:
+            predictor.predict_case({"data": case}, properties, save_dir=target_dir, case_id=case_id, restore=restore)
         else:
+            result = predictor.predict_case({"data": case}, properties, save_dir=None, case_id=None, restore=restore)
+            if result is None:                   # tile sharding: only rank 0 holds the case result
+                continue
+            target_dir.mkdir(parents=True, exist_ok=True)
             for key, item in to_numpy(result).items():
                 save_pickle(item, target_dir / f"{case_id}_{key}.pkl")
     return predictor

@@ -204,8 +204,11 @@ class SlidingWindowPredictor:
                     for k, v in res.items():
                         self.ensembler.model_results[name][k].extend(t.to(dev) for t in v)
 
-    def predict_case(self, case: Dict, properties: Optional[Dict] = None, restore: bool = False) -> Optional[Dict[Hashable, Dict]]:
-        """predictor.py:155-190 (detection branch).  With tile sharding only rank 0 returns the result (others None)."""
+    def predict_case(self, case: Dict, properties: Optional[Dict] = None, save_dir=None, case_id: Optional[str] = None,
+                     restore: bool = False) -> Optional[Dict[Hashable, Dict]]:
+        """predictor.py:155-190 (detection branch), same arguments: with `save_dir` the ensembler state (`<case_id>_boxes.pt`) and the
+        properties (`<case_id>_properties.pkl`) are saved next to returning the result.  With tile sharding only rank 0 saves and
+        returns (others None)."""
         case = dict(case)
         if isinstance(case[self.data_key], Tensor):
             case[self.data_key] = case[self.data_key].to(self.device)
@@ -216,4 +219,13 @@ class SlidingWindowPredictor:
         self.gather_case_result()
         if self.shard[0] != 0:
             return None
-        return {"boxes": self.ensembler.get_case_result(restore=restore)}
+        result = {"boxes": self.ensembler.get_case_result(restore=restore)}
+        if save_dir is not None:                                   # predictor.py:180-185
+            import pickle
+            from pathlib import Path
+            save_dir = Path(save_dir)
+            save_dir.mkdir(parents=True, exist_ok=True)
+            self.ensembler.save_state(save_dir, name=case_id)
+            with open(save_dir / f"{case_id}_properties.pkl", "wb") as f:
+                pickle.dump(properties, f)
+        return result

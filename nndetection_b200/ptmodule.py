@@ -117,5 +117,20 @@ def register_with_reference():
         segmenter_cls = RetinaUNetV001.segmenter_cls
         from_config_plan = classmethod(lambda c, *a, **k: RetinaUNetV001.from_config_plan.__func__(c, *a, **k))
 
+        # inference side: device-resident ensembler and predictor behind the reference's hooks
+        # (`get_ensembler_cls` base.py:677-695, `get_predictor` :697-745); the reference's `predict_dir` / `sweep` call them unchanged
+        @staticmethod
+        def get_ensembler_cls(key, dim):
+            if dim == 3 and key == "boxes":
+                from .inference.ensembler import BoxEnsemblerSelective
+                return BoxEnsemblerSelective
+            return RetinaUNetModule.get_ensembler_cls(key, dim)
+
+        @classmethod
+        def get_predictor(cls, plan, models, num_tta_transforms=None, do_seg=False, **kwargs):
+            from .inference.helper import get_predictor
+            return get_predictor(plan, [getattr(m, "model", m) for m in models], num_tta_transforms, do_seg,
+                                 ensembler_cls=cls.get_ensembler_cls("boxes", plan["network_dim"]), **kwargs)
+
     MODULE_REGISTRY.register(RetinaUNetV001B200)
     return RetinaUNetV001B200
