@@ -27,6 +27,19 @@ extern unsigned long long g_nnd_launches;       // kernels launched through the 
     if (_e != cudaSuccess) return nnd_set_cuda_error(_e, name);         \
   } while (0)
 
+// Function attributes (opt-in shared-memory size) are per DEVICE: a launcher's "already set" flag must be too, or a process that
+// uses a second GPU launches with the default 48 KB limit there.  `need()` is true once per device.
+struct NndPerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 static inline size_t nnd_align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 template <typename T>

@@ -305,11 +305,10 @@ int nnd_conv_first_wgrad_mma(const float* x, const __nv_bfloat16* dy, const Conv
   const int grid = (int)(n_tiles < 2 * NND_NUM_SMS ? n_tiles : 2 * NND_NUM_SMS);
   const int nt = (27 * g.Cin + 7) / 8;
   const size_t smem = (size_t)2 * WZ * WY * WX * 64 + (size_t)2 * g.Cin * WHZ * WHY * WHX * 4 + (size_t)CO * nt * 8 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_first_wgrad_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_first_wgrad_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
   }
   if (g.Cin == 1) conv_first_wgrad_mma_kernel<1><<<grid, 256, smem, st>>>(x, dy, g, dw, tps, (int)n_tiles);
   else conv_first_wgrad_mma_kernel<2><<<grid, 256, smem, st>>>(x, dy, g, dw, tps, (int)n_tiles);

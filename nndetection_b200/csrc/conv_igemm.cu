@@ -274,10 +274,9 @@ int launch_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom
   const int tiles = (Lvox + BM - 1) / BM;
   size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2);
   if (smem < (size_t)BM * (BN + 4) * 4) smem = (size_t)BM * (BN + 4) * 4;      // fp32 output tile of the vector epilogue
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   dim3 grid((unsigned)(tiles * g.N), (unsigned)(ep.CoutPad / BN));
   conv_igemm_kernel<BN><<<grid, THREADS, smem, st>>>(in, w, g, ep, tiles);

@@ -388,10 +388,9 @@ int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g
   tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
   constexpr int HV = (S2 ? 2 * MT + 1 : MT + 2) * HY * HX;
   const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
   conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);

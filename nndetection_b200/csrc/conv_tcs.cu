@@ -354,10 +354,9 @@ int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
   tl.per_nt = g.N * tl.NZ * tl.HB * tl.WB;
   tl.total = tl.per_nt * tl.NT;
   constexpr size_t SMEM = (size_t)9 * (CIN / 8) * WROW + (size_t)A_SLOTS * (CIN / 8) * GP + 8 * (2 * A_SLOTS + 2 * ACC_SLOTS);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_tcs_kernel<CIN, NI, A_SLOTS, LAG, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
   conv_tcs_kernel<CIN, NI, A_SLOTS, LAG, STATS><<<grid, (4 + NI + 4) * 32, SMEM, st>>>(in, w, g, ep, tl);

@@ -243,10 +243,9 @@ int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
   a.rows_per_split = (a.rows_per_split + ROWS - 1) / ROWS * ROWS;
   splits = (a.total_rows + a.rows_per_split - 1) / a.rows_per_split;
   constexpr size_t SMEM = (size_t)STAGES * ((M_T / 8) * ROWS * RW * 16 + (N_T / 8) * ROWS * XW * 16) + 8 * (2 * STAGES + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<N_T, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
   }
   dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(co_tiles * a.ci_tiles));
   conv_wgrad_tc_kernel<N_T, SW><<<grid, WG_THREADS, SMEM, st>>>(a);

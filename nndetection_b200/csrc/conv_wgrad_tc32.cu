@@ -229,10 +229,9 @@ int nnd_conv_wgrad_tc32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const C
   for (int i = 0; i < 27; ++i) a.tw[i] = 255;
   for (int t = 0; t < g.T; ++t) a.tw[(g.off_d[t] + 1) * 9 + (g.off_h[t] + 1) * 3 + (g.off_w[t] + 1)] = g.tap_w[t];
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 8 * (2 * STAGES + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static NndPerDeviceOnce attr_set;
+  if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
   }
   const int grid = a.total < NND_NUM_SMS ? a.total : NND_NUM_SMS;
   conv_wgrad_tc32_kernel<<<grid, THREADS, SMEM, st>>>(a);

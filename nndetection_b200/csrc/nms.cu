@@ -354,11 +354,10 @@ int nms_impl(const float* boxes, const float* scores, long long n, float thr, lo
   dim3 grid((col_blocks + COL_TILES_PER_CTA - 1) / COL_TILES_PER_CTA, col_blocks);
   nms_mask_kernel<DIM><<<grid, TILE, 0, stream>>>(w.sorted, w.vol, ni, col_blocks, thr, w.mask);
   NND_LAUNCH_CHECK("nms_mask_kernel");
-  static bool scan_attr = false;
-  if (!scan_attr) {
+  static NndPerDeviceOnce scan_attr;
+  if (scan_attr.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     NND_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    scan_attr = true;
   }
   // idx_in (the iota input of the sort) is dead by now: reuse it for the sorted-row numbers of the kept boxes
   const int mk = (max_keep < 0 || max_keep > n) ? ni : (int)max_keep;
