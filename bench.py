@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
-    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 / transposed convs), gather_s2 (tcgen05 stride-2 fprop, up-conv dgrad)")
+    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 / transposed convs), gather_s2 (tcgen05 stride-2 fprop, up-conv dgrad), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
     ap.add_argument("--trace-layers", default=None, metavar="CSV",
                     help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
                          "(kernel chosen, layer geometry, ms, GFLOP per launch) -- maps the step time onto the network")
@@ -200,7 +200,7 @@ def main():
     arch, anc, patch, bs = make_plan(args.config)
     torch.manual_seed(1234 + rank)
     net = RetinaUNetV001.from_config_plan(None, arch, anc).to(dev)
-    trainer = Trainer(net, distributed=world > 1)
+    trainer = Trainer(net, distributed=world > 1, bucket_mb=25.0 if "buckets" in args.experimental.split(",") else None)
 
     # ---- synthetic data: 4 distinct batches (> L2: one batch of activations alone is GBs), pinned on the host
     # as many distinct batches as warm-up steps (<= 4): every batch's allocation pattern (it depends on the number of ground-truth

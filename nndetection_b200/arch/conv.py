@@ -72,6 +72,23 @@ class NormParams(nn.Module):
             self.register_parameter("bias", None)
 
 
+_GRAD_OBSERVER = [None]      # object with layer_used(layer) / layer_done(layer), installed by training.GradientBuckets
+
+
+def set_grad_observer(obs):
+    _GRAD_OBSERVER[0] = obs
+
+
+def notify_grad_observer(layer, z):
+    """Gradient-bucket overlap (training.GradientBuckets, opt-in): a layer's parameter gradients are complete when the backward of
+    every one of its uses in this step has run; the autograd node's post-hook fires right after that use's weight-gradient kernels
+    were enqueued on the backward stream."""
+    obs = _GRAD_OBSERVER[0]
+    if obs is not None and z.grad_fn is not None:
+        obs.layer_used(layer)
+        z.grad_fn.register_hook(lambda *_a, _l=layer: obs.layer_done(_l))
+
+
 def _grad_target(param, shape, dev):
     """Where a parameter-gradient kernel accumulates (all of them ADD into their destination).  When the parameter already
     owns a dense fp32 `.grad` (the Trainer's flat gradient buffer, zeroed once per step) the kernels add straight into it
@@ -247,8 +264,10 @@ class BaseConvNormAct(nn.Module):
 
     def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
         n = self.norm
-        return _ConvBlockFn.apply(x, self.conv.weight, self.conv.bias, n.weight if n is not None else None,
-                                  n.bias if n is not None else None, residual, self)
+        z = _ConvBlockFn.apply(x, self.conv.weight, self.conv.bias, n.weight if n is not None else None,
+                               n.bias if n is not None else None, residual, self)
+        notify_grad_observer(self, z)
+        return z
 
     def __deepcopy__(self, memo):                  # planner deep-copies the model (nndet/planning/estimator.py:130)
         import copy

@@ -86,3 +86,102 @@ def test_lr_schedule_matches_reference_scheduler():
         ref = g[f"lrs{i}"]
         mine = np.asarray([poly_lr(s, lr0, int(warm), wlr, gamma, int(n)) for s in range(len(ref))])
         assert np.array_equal(mine, ref), i
+
+
+# ------------------------------------------------------------------ opt-in gradient buckets (training.GradientBuckets)
+class _DirectFn(torch.autograd.Function):
+    """CPU stand-in for arch/conv.py:_ConvBlockFn: y = x * w (per channel); the weight gradient is ADDED straight into `w.grad` (a view
+    of the flat buffer) and autograd gets None for it -- exactly the contract of the direct-accumulation kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, layer):
+        ctx.layer = layer
+        w = weight.detach().view(-1)[:x.shape[1]]
+        ctx.save_for_backward(x, w)
+        return x * w
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        ctx.layer.conv.weight.grad.view(-1)[:x.shape[1]].add_((dy * x).sum(0))
+        return dy * w, None, None
+
+
+def _bucket_model():
+    from nndetection_b200.arch.conv import BaseConvNormAct, notify_grad_observer
+
+    class Direct(BaseConvNormAct):
+        def forward(self, x):
+            z = _DirectFn.apply(x, self.conv.weight, self)
+            notify_grad_observer(self, z)
+            return z
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = Direct(3, 32, 32, None, None, 1)          # 1x1x1 conv holder: weight [32, 32, 1, 1, 1] + bias
+            self.shared = Direct(3, 32, 32, None, None, 1)
+            self.lin = nn.Linear(32, 32)
+            self.b = Direct(3, 32, 32, None, None, 1)
+            self.unused = nn.Parameter(torch.zeros(700))
+
+        def forward(self, x):
+            x = self.a(x)
+            x = self.shared(x)
+            x = torch.tanh(self.lin(x))
+            x = self.shared(x)                                  # second use of the same parameters
+            return self.b(x)
+    return Net()
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nndetection_b200.arch.conv import set_grad_observer
+    from nndetection_b200.training import FlatParameters, GradientBuckets
+    torch.manual_seed(5)
+    model = _bucket_model()
+    fp = FlatParameters(model)
+    torch.manual_seed(50 + rank)
+    x = torch.randn(6, 32)
+
+    def backward_once():
+        fp.zero_grad()
+        (model(x) ** 2).sum().backward()
+
+    backward_once()                                             # reference: one all-reduce after backward
+    ref = fp.grad.clone()
+    dist.all_reduce(ref)
+    gb = GradientBuckets(model, fp, bucket_mb=1000 * 4 / 2 ** 20)          # 1000 floats per bucket -> 5 buckets
+    set_grad_observer(gb)
+    fired = []
+    orig = gb._launch
+    gb._launch = lambda b: (fired.append((b, gb.in_backward)), orig(b))[1]
+    for _ in range(2):                                          # two steps: per-step state resets
+        gb.begin()
+        fired.clear()
+        gb.in_backward = True
+        backward_once()
+        gb.in_backward = False
+        gb.finish()
+        assert torch.equal(fp.grad, ref)
+    set_grad_observer(None)
+    ret[rank] = (list(gb.order), list(fired), len(gb.bounds))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_overlap_gives_the_single_all_reduce_result():
+    """Opt-in bucketed exchange: same gradients as one all-reduce, identical issue order on both ranks, buckets of layers whose
+    backward is over are exchanged DURING backward (the shared layer only after its second use), the rest in finish()."""
+    mp.set_start_method("spawn", force=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() + 7) % 1000
+    procs = [mp.Process(target=_bucket_worker, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(180) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    order0, fired0, nb = ret[0]
+    assert ret[1][0] == order0 and sorted(order0) == list(range(nb)) and nb >= 4
+    during = [b for b, inside in fired0 if inside]
+    assert len(during) >= 2 and any(not inside for _, inside in fired0)       # the bucket with the unused parameter waits for finish()
