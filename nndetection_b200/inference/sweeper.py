@@ -43,42 +43,40 @@ class BoxSweeper:
         self.ensembler_cls = ensembler_cls
 
     def run_postprocessing_sweep(self) -> Dict[str, Any]:
-        """sweeper.py:112-141: the determined parameters (the plan's `inference_plan`)."""
-        state, sweep_params = self.ensembler_cls.sweep_parameters()
-        for param_name, values in sweep_params.items():
-            best_value, _ = self.run_parameter(values=values, param_name=param_name, state=state)
-            state[param_name] = best_value
+        """sweeper.py:112-141: the determined parameters (the plan's `inference_plan`).  Coordinate-wise: each parameter is searched
+        with the winners of the earlier ones already fixed in `state`."""
+        state, grid = self.ensembler_cls.sweep_parameters()
+        for name in grid:
+            state[name] = self.run_parameter(values=grid[name], param_name=name, state=state)[0]
         return state
 
     def run_parameter(self, values: Sequence[Any], param_name: str, state: Dict[str, Any]) -> Tuple[Any, float]:
-        """sweeper.py:143-178."""
-        cache, overview = [], {}
-        for value in values:
-            tic = time.perf_counter()
-            metric_scores = self._evaluate_value(state=state, **{param_name: value})
-            overview[f"{param_name}_{value}".replace(".", "_")] = {
-                "state": str(state), "overwrite": {param_name: str(value)}, "scores": str(metric_scores),
-                "seconds": time.perf_counter() - tic}
-            cache.append(metric_scores[self.target_metric])
-        best_idx = int(np.argmax(cache))
-        best_value, best_score = values[best_idx], cache[best_idx]
+        """sweeper.py:143-178: score every candidate value of one parameter, first best wins; the per-value report goes to
+        `<save_dir>/sweep_<param_name>.json` (same keys as the reference's file + the seconds each evaluation took)."""
+        report, scores = {}, []
+        for candidate in values:
+            started = time.perf_counter()
+            metrics = self._evaluate_value(state=state, **{param_name: candidate})
+            scores.append(metrics[self.target_metric])
+            report[f"{param_name}_{candidate}".replace(".", "_")] = dict(
+                state=str(state), overwrite={param_name: str(candidate)}, scores=str(metrics), seconds=time.perf_counter() - started)
+        winner = int(np.argmax(scores))
         if self.save_dir is not None:
-            overview[f"best_{param_name}"] = {"value": str(best_value), "score": str(best_score)}
-            with open(self.save_dir / f"sweep_{param_name}.json", "w") as f:
-                json.dump(overview, f, indent=4)
-        return best_value, best_score
+            report[f"best_{param_name}"] = dict(value=str(values[winner]), score=str(scores[winner]))
+            (self.save_dir / f"sweep_{param_name}.json").write_text(json.dumps(report, indent=4))
+        return values[winner], scores[winner]
 
     def _evaluate_value(self, state: Dict[str, Any], **overwrite) -> Dict[str, float]:
-        """sweeper.py:180-216."""
+        """sweeper.py:180-216: every case's saved state is restored (onto `self.device`), post-processed with `state` + `overwrite`,
+        and handed to a fresh evaluator together with its ground truth."""
         evaluator = self.evaluator_cls.create(classes=self.classes, fast=True, verbose=False, save_dir=None)
+        settings = dict(state, **overwrite)
         for case_id in self.ensembler_cls.get_case_ids(self.pred_dir):
-            ensembler = self.ensembler_cls.from_checkpoint(base_dir=self.pred_dir, case_id=case_id, device=self.device)
-            ensembler.update_parameters(**state)
-            ensembler.update_parameters(**overwrite)
-            pred = to_numpy(ensembler.get_case_result(restore=False))
-            gt = np.load(str(self.gt_dir / f"{case_id}_boxes_gt.npz"), allow_pickle=True)
-            evaluator.run_online_evaluation(
-                pred_boxes=[pred["pred_boxes"]], pred_classes=[pred["pred_labels"]], pred_scores=[pred["pred_scores"]],
-                gt_boxes=[gt["boxes"]], gt_classes=[gt["classes"]], gt_ignore=None)
-        metric_scores, _ = evaluator.finish_online_evaluation()
-        return metric_scores
+            ens = self.ensembler_cls.from_checkpoint(base_dir=self.pred_dir, case_id=case_id, device=self.device)
+            ens.update_parameters(**settings)
+            det = to_numpy(ens.get_case_result(restore=False))
+            truth = np.load(str(self.gt_dir / f"{case_id}_boxes_gt.npz"), allow_pickle=True)
+            evaluator.run_online_evaluation(pred_boxes=[det["pred_boxes"]], pred_classes=[det["pred_labels"]],
+                                            pred_scores=[det["pred_scores"]], gt_boxes=[truth["boxes"]],
+                                            gt_classes=[truth["classes"]], gt_ignore=None)
+        return evaluator.finish_online_evaluation()[0]
