@@ -39,3 +39,6 @@ for args in "32 64 128 4" "64 128 64 4" "128 256 32 4"; do
 done | tee gpurun_out/strided_layers.txt
 # BASELINE config 4 through the predictor + ensembler (one 288^3 case, 160^3 patches, 8 mirror passes)
 timeout 300 python scripts/bench_inference.py > gpurun_out/bench_inference.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_inference.json
+# CTA-pair probe (cta_group::2 semantics + issue rate) for the round-2 128-channel kernels; a hang only costs its timeout
+if [ ! -x scripts/pair_probe ]; then nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I nndetection_b200/csrc -o scripts/pair_probe scripts/pair_probe.cu; fi
+timeout 60 scripts/pair_probe 2>&1 | tee gpurun_out/pair_probe.txt
