@@ -133,6 +133,12 @@ void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming
 void nnd_conv_trace(int enable);
 long long nnd_conv_trace_count(void);
 int nnd_conv_trace_dump(const char* path);
+/* Dry-run dispatch queries (host only, no CUDA call): the kernel that would serve a launch under the current switches.
+ * gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2 (opt-in); wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
+ * 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2 (opt-in); negative: bad geometry. */
+int nnd_conv_gather_dispatch(const int* geom_host, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
+                             int has_bias, int has_residual, int has_stats);
+int nnd_conv_wgrad_dispatch(const int* geom_host, int Cdy, int Cx);
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);

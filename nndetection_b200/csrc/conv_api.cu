@@ -140,6 +140,36 @@ int nnd_conv_trace_dump(const char* path) {
   return NND_OK;
 }
 
+// Dry-run dispatch queries (host only, no CUDA call -- usable without a GPU): which kernel would serve this launch under the current
+// switches.  gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2; wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
+// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2.  Negative: bad geometry.
+int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
+                             int has_bias, int has_residual, int has_stats) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return -1;
+  static float dummy;
+  ConvEpilogue ep;
+  ep.out = &dummy; ep.out_n_stride = out_n_stride; ep.out_v_stride = out_v_stride; ep.out_fp32 = out_fp32;
+  ep.Cout = Cout; ep.CoutPad = CoutPad; ep.bias = has_bias ? &dummy : nullptr; ep.scale = nullptr;
+  ep.residual = has_residual ? reinterpret_cast<const __nv_bfloat16*>(&dummy) : nullptr;
+  ep.stat_sum = has_stats ? &dummy : nullptr; ep.stat_sq = has_stats ? &dummy : nullptr;
+  if (g_force_igemm) return 0;
+  if (g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) return 2;
+  if (g_gather_strided && nnd_conv_tc_s2_supported(g, ep)) return 3;
+  return nnd_conv_tc_supported(g, ep) ? 1 : 0;
+}
+
+int nnd_conv_wgrad_dispatch(const int* geom, int Cdy, int Cx) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return -1;
+  if (g_force_igemm) return 0;
+  if (g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) return 3;
+  if (g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) return 4;
+  if (g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) return 2;
+  if (g_wgrad_tc && g_wgrad_strided && nnd_conv_wgrad_tc_strided_supported(g, Cdy, Cx)) return 5;
+  return nnd_conv_wgrad_halo_supported(g, Cdy, Cx) ? 1 : 0;
+}
+
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st) {
