@@ -121,7 +121,7 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
  *      (csrc/conv_common.cuh): N,Di,Hi,Wi,Cin, Ld,Lh,Lw, sd,sh,sw, Do,Ho,Wo, omd,omh,omw, ood,ooh,oow, T, then per tap
  *      (off_d, off_h, off_w, weight_tap).  w: bf16 [T][CoutPad][Cin] from nnd_pack_weights.  Epilogue: +bias, +residual,
  *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
- *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel, 3 tcgen05 stride-2 tile kernel (opt-in). */
+ *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel, 3 tcgen05 stride-2 tile kernel (opt-in), 4 tcgen05 tile kernel with bulk-copied weights (opt-in). */
 void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_wgrad_strided_tc(int enable);       /* opt-in (default 0): de-interleaved tcgen05 wgrad for stride-2 convolutions, not yet validated on a device */
@@ -142,6 +142,15 @@ int nnd_conv_wgrad_dispatch(const int* geom_host, int Cdy, int Cx);
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);
+/* Opt-in (default off, not yet validated on a device): the tile kernel's weight stream through cp.async.bulk.  The caller re-packs a
+ * K-major weight pack [T][rows_pad][K] into pipeline-item order [row tile][k chunk][T][k group][n][8] (kg = 4: 32-channel chunks)
+ * and passes it along with the ordinary pack; used only while nnd_conv_set_tc_bulk(1). */
+void nnd_conv_set_tc_bulk(int enable);
+int nnd_repack_items_bf16(const void* src, int T, int rows_pad, int K, int n_tile, int kg, void* dst, cudaStream_t stream);
+int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
+                               long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
+                               const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream,
+                               const void* w_items, int items_n_tile, int items_T);
 /* dW[co*s_co + ci*s_ci + tap*s_tap] += sum_voxels dy[.., co] * x[.., ci]   (fp32, caller zero-fills) */
 int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom_host, float* dw, long long s_co,
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t stream);

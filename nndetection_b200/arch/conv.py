@@ -125,10 +125,11 @@ class _ConvBlockFn(torch.autograd.Function):
             ops.conv_first_fprop(x, weight.detach(), plan.fprop[0], cout, y, stats[0] if has_norm else None,
                                  stats[1] if has_norm else None)
         else:
+            items_f = layer.packed_items()[0]
             for g in plan.fprop:
                 ops.conv_gather(x, wp_f, g, y, cout, pad32(cout), bias=bias.detach() if bias is not None else None,
                                 residual=res, stat_sum=stats[0] if has_norm else None,
-                                stat_sq=stats[1] if has_norm else None)
+                                stat_sq=stats[1] if has_norm else None, w_items=items_f)
         V = plan.out_sp[0] * plan.out_sp[1] * plan.out_sp[2]
         if has_norm:
             a, b, mean, rstd = ops.norm_finalize(stats[0], stats[1], gamma.detach() if gamma is not None else None,
@@ -187,8 +188,9 @@ class _ConvBlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[0] and not layer.is_first:
             _, wp_b = layer.packed()
             dx = (ops.empty_cl if plan.dgrad_covers_all else ops.zeros_cl)(N, cin, plan.in_sp, device=dev)
+            items_b = layer.packed_items()[1]
             for g in plan.dgrad:
-                ops.conv_gather(dy, wp_b, g, dx, cin, pad32(cin))
+                ops.conv_gather(dy, wp_b, g, dx, cin, pad32(cin), w_items=items_b)
         dres = dy if ctx.has_res else None
         if has_norm and gamma is not None:
             dgamma, dbeta = dgamma_ret, dbeta_ret
@@ -260,7 +262,18 @@ class BaseConvNormAct(nn.Module):
             else:
                 self._packed = ops.pack_weights(w.detach(), c.out_channels, c.in_channels, T, c.transposed)
             self._packed_key = key
+            self._items = None
         return self._packed
+
+    def packed_items(self):
+        """(fprop, dgrad) `ItemPack`s of the current weights for the opt-in bulk-copy variant of the tile kernel, or (None, None):
+        refreshed together with `packed()`; only built while that variant is switched on."""
+        if not ops.tc_bulk_enabled() or self.is_first:
+            return None, None
+        wp_f, wp_b = self.packed()
+        if getattr(self, "_items", None) is None:
+            self._items = (ops.repack_items(wp_f) if wp_f is not None else None, ops.repack_items(wp_b) if wp_b is not None else None)
+        return self._items
 
     def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
         n = self.norm
@@ -275,7 +288,7 @@ class BaseConvNormAct(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_plans", "_packed", "_packed_key"):
+            if k in ("_plans", "_packed", "_packed_key", "_items"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._plans, new._packed, new._packed_key = {}, None, None

@@ -104,18 +104,66 @@ class ConvPlan:
 
 
 def conv_gather(x: Tensor, w_packed: Tensor, geom, out: Tensor, cout: int, cout_pad: int, *, out_fp32=False,
-                out_n_stride=None, out_v_stride=None, bias=None, scale=None, residual=None, stat_sum=None, stat_sq=None):
-    """One launch of the gather convolution.  `out` may be any tensor whose data_ptr is the destination base."""
+                out_n_stride=None, out_v_stride=None, bias=None, scale=None, residual=None, stat_sum=None, stat_sq=None,
+                w_items=None):
+    """One launch of the gather convolution.  `out` may be any tensor whose data_ptr is the destination base.
+    w_items: optional `ItemPack` of the same weights (opt-in bulk-copy variant of the tile kernel)."""
     used = c_int(0)
     if out_n_stride is None:
         out_n_stride = geom[11] * geom[12] * geom[13] * cout
     if out_v_stride is None:
         out_v_stride = cout
-    L.check(L.lib().nnd_conv_gather_bf16(L.ptr(x), L.ptr(w_packed), geom, L.ptr(out), c_longlong(out_n_stride),
-                                         c_longlong(out_v_stride), c_int(1 if out_fp32 else 0), c_int(cout),
-                                         c_int(cout_pad), L.ptr(bias), L.ptr(scale), L.ptr(residual), L.ptr(stat_sum),
-                                         L.ptr(stat_sq), byref(used), L.stream_ptr()), "nnd_conv_gather_bf16")
+    if w_items is None:
+        L.check(L.lib().nnd_conv_gather_bf16(L.ptr(x), L.ptr(w_packed), geom, L.ptr(out), c_longlong(out_n_stride),
+                                             c_longlong(out_v_stride), c_int(1 if out_fp32 else 0), c_int(cout),
+                                             c_int(cout_pad), L.ptr(bias), L.ptr(scale), L.ptr(residual), L.ptr(stat_sum),
+                                             L.ptr(stat_sq), byref(used), L.stream_ptr()), "nnd_conv_gather_bf16")
+    else:
+        L.check(L.lib().nnd_conv_gather_bf16_items(L.ptr(x), L.ptr(w_packed), geom, L.ptr(out), c_longlong(out_n_stride),
+                                                   c_longlong(out_v_stride), c_int(1 if out_fp32 else 0), c_int(cout),
+                                                   c_int(cout_pad), L.ptr(bias), L.ptr(scale), L.ptr(residual), L.ptr(stat_sum),
+                                                   L.ptr(stat_sq), byref(used), L.stream_ptr(), L.ptr(w_items.data),
+                                                   c_int(w_items.n_tile), c_int(w_items.T)), "nnd_conv_gather_bf16_items")
     return used.value
+
+
+class ItemPack:
+    """A K-major weight pack [T][rows_pad][K] re-ordered for the bulk-copy variant of the tile kernel: [row tile][k chunk][T][k group]
+    [n][8] -- the slice one pipeline item needs (one tap, one 32-channel chunk, one n_tile-row tile) is contiguous."""
+
+    def __init__(self, data: Tensor, n_tile: int, T: int):
+        self.data, self.n_tile, self.T = data, n_tile, T
+
+
+def item_n_tile(rows_pad: int) -> int:
+    """The row tile the tile kernel uses for `rows_pad` output channels (csrc/conv_tc.cu: nnd_conv_tc)."""
+    return 128 if rows_pad % 128 == 0 else (64 if rows_pad % 64 == 0 else 32)
+
+
+def repack_items(w_packed: Tensor) -> Optional["ItemPack"]:
+    """w_packed: bf16 [T][rows_pad][K] (fprop or dgrad pack of `pack_weights`).  None when the shape cannot take the bulk path."""
+    T, rows_pad, K = (int(v) for v in w_packed.shape)
+    if K % 32 or rows_pad % 32:
+        return None
+    n_tile = item_n_tile(rows_pad)
+    out = torch.empty_like(w_packed)
+    L.check(L.lib().nnd_repack_items_bf16(L.ptr(w_packed), c_int(T), c_int(rows_pad), c_int(K), c_int(n_tile), c_int(4), L.ptr(out),
+                                          L.stream_ptr()), "nnd_repack_items_bf16")
+    return ItemPack(out, n_tile, T)
+
+
+_TC_BULK = False
+
+
+def set_tc_bulk(enable: bool):
+    """Opt-in: the tile kernel's weight stream through cp.async.bulk on item-order packs (not yet validated on a device; default off)."""
+    global _TC_BULK
+    L.lib().nnd_conv_set_tc_bulk(c_int(1 if enable else 0))
+    _TC_BULK = bool(enable)
+
+
+def tc_bulk_enabled() -> bool:
+    return _TC_BULK
 
 
 def conv_wgrad(dy: Tensor, cdy: int, x: Tensor, cx: int, geom, dw: Tensor, s_co: int, s_ci: int, s_tap: int, cout: int,

@@ -13,6 +13,9 @@ int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom&
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tc_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tc_bulk_supported(const ConvGeom& g, const ConvEpilogue& ep, const void* items, int items_n_tile, int items_T);
+int nnd_conv_tc_bulk(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st,
+                     const __nv_bfloat16* items, int items_n_tile, int items_T);
 int nnd_conv_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tcs_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tcs_profitable(const ConvGeom& g, const ConvEpilogue& ep);
@@ -58,6 +61,7 @@ int g_wgrad_tc = 1;
 int g_stream = 1;
 int g_wgrad_strided = 0;
 int g_gather_strided = 0;
+int g_tc_bulk = 0;
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
 // ncu names kernels, not layers; this table is what maps the step time onto the network.
@@ -104,6 +108,9 @@ void nnd_conv_set_wgrad_strided_tc(int enable) { g_wgrad_strided = enable; }
 // 1: stride-2 gathers (3x3x3 stride-2 convolutions, dgrad of up-convolutions) take the de-interleaved-halo tcgen05 tile kernel
 // (conv_tc.cu, S2 = 1) instead of the mma.sync kernel.  Default 0 until validated on a B200 (written without one).
 void nnd_conv_set_gather_strided_tc(int enable) { g_gather_strided = enable; }
+// 1: launches that bring an item-order weight pack (nnd_conv_gather_bf16_items) stream it with cp.async.bulk (conv_tc.cu, BULK = 1).
+// Default 0 until validated on a B200 (written without one).
+void nnd_conv_set_tc_bulk(int enable) { g_tc_bulk = enable; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -170,9 +177,24 @@ int nnd_conv_wgrad_dispatch(const int* geom, int Cdy, int Cx) {
   return nnd_conv_wgrad_halo_supported(g, Cdy, Cx) ? 1 : 0;
 }
 
+int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
+                               long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
+                               const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st,
+                               const void* w_items, int items_n_tile, int items_T);
+
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st) {
+  return nnd_conv_gather_bf16_items(in, w, geom, out, out_n_stride, out_v_stride, out_fp32, Cout, CoutPad, bias, scale, residual,
+                                    stat_sum, stat_sq, used_tc, st, nullptr, 0, 0);
+}
+
+// Same launch; `w_items` optionally carries the weights a second time, re-packed in pipeline-item order by nnd_repack_items_bf16 for
+// tiles of `items_n_tile` rows (`items_T` weight slices): used by the opt-in bulk-copy variant of the tile kernel, ignored otherwise.
+int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, void* out, long long out_n_stride,
+                               long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
+                               const void* residual, float* stat_sum, float* stat_sq, int* used_tc, cudaStream_t st,
+                               const void* w_items, int items_n_tile, int items_T) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
   ConvEpilogue ep;
@@ -188,6 +210,11 @@ int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom, void* o
     if (used_tc) *used_tc = 3;
     TraceScope ts("fprop", "conv_tc_s2", g, g.Cin, Cout, st);
     return nnd_conv_tc_s2((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+  }
+  if (!g_force_igemm && g_tc_bulk && nnd_conv_tc_bulk_supported(g, ep, w_items, items_n_tile, items_T)) {
+    if (used_tc) *used_tc = 4;
+    TraceScope ts("fprop", "conv_tc_bulk", g, g.Cin, Cout, st);
+    return nnd_conv_tc_bulk((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st, (const __nv_bfloat16*)w_items, items_n_tile, items_T);
   }
   const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
   if (used_tc) *used_tc = tc ? 1 : 0;

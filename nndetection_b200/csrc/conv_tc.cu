@@ -25,6 +25,13 @@
 // 0..n, "even" plane (2p, p = 0..n-1) in slots n+1..2n -- so that the 8 (w) x 16 (h) x MT (d) voxels a tap multiplies are again
 // consecutive slots: off = -1 -> slot 0, off = 0 -> slot n + 1, off = +1 -> slot 1 of that axis.  16 channels per chunk
 // (the halo is 8x the tile instead of 1.7x), one K = 16 MMA per tap and depth slice.
+//
+// BULK = 1 (opt-in until validated on the device, nnd_conv_set_tc_bulk): the weight stream through the bulk-copy engine.  At
+// ~700 TFLOP/s the 128-channel layers move only ~6 B/clk/SM of operands: they are bound by the producers' per-item work (hundreds of
+// 16-byte cp.async + wait_group / fence / arrive bookkeeping per 8 KB slice), not by bandwidth.  With the weights re-packed in item
+// order ONE thread posts `mbarrier.arrive.expect_tx` and TG `cp.async.bulk` copies per item (the barrier completes on the bytes,
+// written through the async proxy the MMA reads through: no fence); the halo gets its own FULLA barrier (the producers block on
+// `cp.async.wait_group 0` right after issuing it -- they have nothing else to do any more).
 #include "conv_common.cuh"
 #include "tcgen05.cuh"
 
@@ -43,11 +50,23 @@ constexpr int tc_threads(int mt) { return (4 + mt + 4) * 32; }   // 4 producer +
 struct TcTiles {
   int DB, HB, WB, NT;       // tile counts along d, h, w and output-channel tiles
   int total;
+  // BULK variant only: the weights again, re-packed in pipeline-item order [co tile][ci chunk][weight slice][k group][n][8]
+  // (one tap slice of one chunk = B_TAP_BYTES contiguous bytes) and the number of weight slices of the pack
+  const __nv_bfloat16* items;
+  int items_T;
 };
 
 
 // TG = taps per pipeline item (weight slices loaded / consumed together), ACC = TMEM accumulator stages
-template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2>
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2, int BULK>
 __global__ void __launch_bounds__(tc_threads(MT), 1)
 conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ wgt, const ConvGeom g,
                const ConvEpilogue ep, const TcTiles tl) {
@@ -82,13 +101,15 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   auto EMPTYA = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + i); };
   auto TFULL = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + i); };
   auto TEMPTY = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + 2 + i); };
+  auto FULLA = [&](int i) { return bar0 + 8u * (2 * B_SLOTS + A_STAGES + 4 + i); };      // BULK only
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = g.Cin / (8 * KG), T = g.T;
 
   if (tid == 0) {
-    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), NUM_PROD / 32); mbar_init(EMPTYB(i), MT); }
+    for (int i = 0; i < B_SLOTS; ++i) { mbar_init(FULLB(i), BULK ? 1 : NUM_PROD / 32); mbar_init(EMPTYB(i), MT); }
     for (int i = 0; i < A_STAGES; ++i) mbar_init(EMPTYA(i), MT);
+    if (BULK) for (int i = 0; i < A_STAGES; ++i) mbar_init(FULLA(i), NUM_PROD / 32);
     for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), MT); mbar_init(TEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -137,8 +158,10 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const int kc = chunk % KC;
       int n, d0, h0, w0, nt;
       decode_tile(tile, n, d0, h0, w0, nt);
-      const bool a_free = __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(EMPTYA(astage), a_phase ^ 1) : 0, 0) != 0;
-      if (!a_free) {
+      const bool a_free = BULK ? false : __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(EMPTYA(astage), a_phase ^ 1) : 0, 0) != 0;
+      if (BULK) {
+        mbar_wait_warp(EMPTYA(astage), a_phase ^ 1, lane);      // no arrivals are ever owed in this variant: just wait
+      } else if (!a_free) {
         // The halo buffer is still being read.  Its release needs the MMAs of the previous chunk, which may be
         // waiting for weight items whose (deferred) arrival this warp still owes: publish them before blocking.
         cp_async_wait<0>();
@@ -184,6 +207,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
           }
         }
       }
+      if (BULK) {                                   // publish the halo on its own barrier as soon as it has landed
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(FULLA(astage));
+      }
       astage ^= 1; if (astage == 0) a_phase ^= 1;
     };
 
@@ -194,6 +224,23 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       const __nv_bfloat16* wbase = wgt + (size_t)(nt * N_TILE) * g.Cin + kc * (8 * KG);
       for (int it = 0; it < NI_ITEMS; ++it) {
         mbar_wait_warp(EMPTYB(slot), slot_phase ^ 1, lane);
+        if (BULK) {
+          // weights first (one thread, TG bulk copies onto the slot's barrier), then -- if one is due -- the halo, on which all
+          // producer warps block until it has landed
+          if (tid == 0) {
+            const unsigned b_base = smem_u32(sB + slot * B_BYTES);
+            mbar_expect_tx(FULLB(slot), B_BYTES);
+#pragma unroll
+            for (int tt = 0; tt < TG; ++tt) {
+              const size_t slice = ((size_t)(nt * KC + kc) * tl.items_T + g.tap_w[it * TG + tt]) * (B_TAP_BYTES / 2);
+              bulk_g2s(b_base + tt * B_TAP_BYTES, tl.items + slice, B_TAP_BYTES, FULLB(slot));
+            }
+          }
+          if (chunk == 0 && it == 0) load_halo(0);
+          if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
+          if (++slot == B_SLOTS) { slot = 0; slot_phase ^= 1; }
+          continue;
+        }
         if (chunk == 0 && it == 0) load_halo(0);
         if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
         {
@@ -233,11 +280,13 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
     if (lane == 0) {
       const int mt = warp - 4;
       unsigned slot = 0, slot_phase = 0, astage = 0, acc = 0, acc_phase = 0;
+      unsigned afull_phase = 0;                      // BULK: phase of FULLA[astage]
       for (int tile = blockIdx.x; tile < tl.total; tile += gridDim.x) {
         mbar_wait(TEMPTY(acc), acc_phase ^ 1);
         tc_fence_after();
         const unsigned d_tmem = tmem_base + acc * ACC_COLS + mt * N_TILE;
         for (int kc = 0; kc < KC; ++kc) {
+          if (BULK) { mbar_wait(FULLA(astage), afull_phase); tc_fence_after(); }
           // only the 14-bit start-address field changes between MMAs: add (byte offset >> 4) to a base descriptor
           const unsigned long long a_desc0 = make_desc(smem_u32(sA + astage * A_BYTES) + mt * SLICE_PITCH, LBO_A, SBO_A);
           for (int it = 0; it < T / TG; ++it) {
@@ -257,6 +306,7 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
           }
           tc_commit(EMPTYA(astage));
           astage ^= 1;
+          if (BULK && astage == 0) afull_phase ^= 1;
         }
         tc_commit(TFULL(acc));
         if (ACC == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; } else acc_phase ^= 1;
@@ -379,21 +429,23 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
   }
 }
 
-template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2 = 0>
-int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2 = 0, int BULK = 0>
+int launch_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st,
+              const __nv_bfloat16* items = nullptr, int items_T = 0) {
   constexpr int KG = S2 ? 2 : ::KG;
   constexpr int HY = S2 ? 2 * BH + 1 : ::HY, HX = S2 ? 2 * BW + 1 : ::HX;
   TcTiles tl;
   tl.DB = (g.Ld + MT - 1) / MT; tl.HB = (g.Lh + BH - 1) / BH; tl.WB = (g.Lw + BW - 1) / BW; tl.NT = ep.CoutPad / N_TILE;
   tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
+  tl.items = items; tl.items_T = items_T;
   constexpr int HV = (S2 ? 2 * MT + 1 : MT + 2) * HY * HX;
-  const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4);
+  const size_t smem = (size_t)A_STAGES * KG * HV * 16 + (size_t)B_SLOTS * TG * N_TILE * KG * 16 + 8 * (2 * B_SLOTS + A_STAGES + 4 + (BULK ? A_STAGES : 0));
   static NndPerDeviceOnce attr_set;
   if (attr_set.need()) {
-    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NND_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int grid = tl.total < NND_NUM_SMS ? tl.total : NND_NUM_SMS;
-  conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
+  conv_tc_kernel<N_TILE, MT, TG, ACC, B_SLOTS, S2, BULK><<<grid, tc_threads(MT), smem, st>>>(in, w, g, ep, tl);
   NND_LAUNCH_CHECK("conv_tc_kernel");
   return NND_OK;
 }
@@ -443,6 +495,28 @@ int nnd_conv_tc_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGe
   if (ep.CoutPad % 128 == 0) return g3 ? launch_tc<128, 2, 3, 2, 3, 1>(in, w, g, ep, st) : launch_tc<128, 2, 1, 2, 8, 1>(in, w, g, ep, st);
   if (ep.CoutPad % 64 == 0) return g3 ? launch_tc<64, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tc<64, 2, 1, 2, 8, 1>(in, w, g, ep, st);
   return g3 ? launch_tc<32, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tc<32, 2, 1, 2, 8, 1>(in, w, g, ep, st);
+}
+
+// BULK variant: the 3-taps-per-item instantiations of the stride-1 kernel with the item-order weight pack (see the header comment).
+// items_n_tile: the N_TILE the pack was made for (must be the one the dispatch below picks), items_T: weight slices in the pack.
+int nnd_conv_tc_bulk_supported(const ConvGeom& g, const ConvEpilogue& ep, const void* items, int items_n_tile, int items_T) {
+  if (!items || !nnd_conv_tc_supported(g, ep) || g.T % 3 != 0 || g_tc_deep_ring != 2) return 0;
+  const int n_tile = ep.CoutPad % 128 == 0 ? 128 : (ep.CoutPad % 64 == 0 ? 64 : 32);
+  if (items_n_tile != n_tile || ((size_t)items & 15)) return 0;
+  for (int t = 0; t < g.T; ++t) if (g.tap_w[t] >= items_T) return 0;
+  return 1;
+}
+
+int nnd_conv_tc_bulk(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st,
+                     const __nv_bfloat16* items, int items_n_tile, int items_T) {
+  if (!nnd_conv_tc_bulk_supported(g, ep, items, items_n_tile, items_T)) return NND_ERR_ARG;
+  if (ep.CoutPad % 128 == 0) {
+    const long long tiles4 = (long long)g.N * ((g.Ld + 3) / 4) * ((g.Lh + BH - 1) / BH) * ((g.Lw + BW - 1) / BW) * (ep.CoutPad / 128);
+    if (tiles4 >= NND_NUM_SMS) return launch_tc<128, 4, 3, 1, 3, 0, 1>(in, w, g, ep, st, items, items_T);
+    return launch_tc<128, 2, 3, 2, 4, 0, 1>(in, w, g, ep, st, items, items_T);
+  }
+  if (ep.CoutPad % 64 == 0) return launch_tc<64, 4, 3, 2, 6, 0, 1>(in, w, g, ep, st, items, items_T);
+  return launch_tc<32, 4, 3, 2, 6, 0, 1>(in, w, g, ep, st, items, items_T);
 }
 
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {

@@ -25,6 +25,22 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
   }
 }
 
+// K-major pack [T][rows_pad][K] (bf16) -> pipeline-item order [row tile][k chunk][T][k group][n][8]: one tap slice of one
+// (8 * kg)-channel chunk and one n_tile-row tile becomes n_tile * kg * 16 contiguous bytes -- the unit conv_tc.cu's BULK variant
+// fetches with one cp.async.bulk.  One thread moves one 16-byte group.
+__global__ void repack_items_kernel(const uint4* __restrict__ src, int T, int rows_pad, int K, int n_tile, int kg, uint4* __restrict__ dst) {
+  const int KC = K / (8 * kg), NT = rows_pad / n_tile;
+  const long long total = (long long)T * rows_pad * (K / 8);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;            // destination index in 16-byte groups
+  if (i >= total) return;
+  const int n = (int)(i % n_tile); long long r = i / n_tile;
+  const int g = (int)(r % kg); r /= kg;
+  const int t = (int)(r % T); r /= T;
+  const int kc = (int)(r % KC); const int nt = (int)(r / KC);
+  if (nt >= NT) return;
+  dst[i] = src[((long long)t * rows_pad + (nt * n_tile + n)) * (K / 8) + kc * kg + g];
+}
+
 // torch.optim.SGD(momentum, nesterov, weight_decay) on a flat fp32 buffer; elements >= n_decay get no weight decay
 // (norm parameters, nndet/training/optimizer/utils.py).  first_step: momentum buffer initialised with the gradient.
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, long long n,
@@ -143,6 +159,14 @@ int nnd_pack_weights(const float* w, int Cout, int Cin, int T, int transposed, v
   pack_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, Cout, Cin, T, transposed, (__nv_bfloat16*)fwd, CoutPadF,
                                                                    CinPadF, (__nv_bfloat16*)bwd, CinPadB, CoutPadB);
   NND_LAUNCH_CHECK("pack_weights_kernel");
+  return NND_OK;
+}
+
+int nnd_repack_items_bf16(const void* src, int T, int rows_pad, int K, int n_tile, int kg, void* dst, cudaStream_t st) {
+  if (!src || !dst || T <= 0 || n_tile <= 0 || kg <= 0 || rows_pad % n_tile || K % (8 * kg)) return NND_ERR_ARG;
+  const long long total = (long long)T * rows_pad * (K / 8);
+  repack_items_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)src, T, rows_pad, K, n_tile, kg, (uint4*)dst);
+  NND_LAUNCH_CHECK("repack_items_kernel");
   return NND_OK;
 }
 

@@ -302,3 +302,25 @@ def test_dispatch_table_of_the_luna_train_step():
     assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")         # stride-1 layers untouched
     _, _, frac_after = dr.report("luna", experimental=False, quiet=True)
     assert frac_after == frac                                                                      # switches restored
+
+
+def test_item_order_weight_pack_layout():
+    """Layout contract between `repack_items_kernel` (csrc/misc.cu) and the BULK producer of csrc/conv_tc.cu, in numpy: destination
+    16-byte group i = (((nt * KC + kc) * T + t) * kg + g) * n_tile + n  <-  source group ((t * rows_pad + nt * n_tile + n) * K / 8 +
+    kc * kg + g); the producer fetches slice (nt, kc, t) = n_tile * kg groups starting at ((nt * KC + kc) * T + t) * n_tile * kg and the
+    MMA's B operand layout inside a slice is [k group][n][8]."""
+    T, rows_pad, K, n_tile, kg = 27, 256, 64, 128, 4
+    src = np.arange(T * rows_pad * K, dtype=np.int64).reshape(T, rows_pad, K // 8, 8)            # element ids, 8 per 16-byte group
+    KC, NT = K // (8 * kg), rows_pad // n_tile
+    dst = np.empty((T * rows_pad * K // 8, 8), dtype=np.int64)
+    i = np.arange(dst.shape[0])
+    n = i % n_tile; r = i // n_tile
+    g = r % kg; r //= kg
+    t = r % T; r //= T
+    kc = r % KC; nt = r // KC
+    dst[i] = src[t, nt * n_tile + n, kc * kg + g]
+    for (nt_, kc_, t_) in [(0, 0, 0), (1, 1, 26), (1, 0, 13)]:
+        start = ((nt_ * KC + kc_) * T + t_) * n_tile * kg
+        sl = dst[start:start + n_tile * kg].reshape(kg, n_tile, 8)                                # what one bulk copy lands in smem
+        want = src[t_, nt_ * n_tile:(nt_ + 1) * n_tile, kc_ * kg:(kc_ + 1) * kg].transpose(1, 0, 2)   # [k group][n][8] of that tap / chunk / tile
+        assert np.array_equal(sl, want)

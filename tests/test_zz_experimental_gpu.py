@@ -148,3 +148,49 @@ def test_upconv_input_gradient_on_tcgen05(cin, cout, shape):
     assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
     assert rel_err(res[True][0], xr.grad) < 5e-3
     assert rel_err(res[True][0], res[False][0]) < 3e-3
+
+
+def test_item_order_repack_kernel():
+    """nnd_repack_items_bf16 against the same permutation in torch."""
+    from nndetection_b200.arch import conv_ops as ops
+    g = torch.Generator().manual_seed(65)
+    for T, rows, K in [(27, 256, 64), (27, 128, 128), (9, 64, 320 - 320 % 32), (27, 32, 32)]:
+        w = torch.randn(T, rows, K, generator=g).to(torch.bfloat16).cuda()
+        ip = ops.repack_items(w)
+        nt_, kc_ = rows // ip.n_tile, K // 32
+        want = w.view(T, nt_, ip.n_tile, kc_, 4, 8).permute(1, 3, 0, 4, 2, 5).contiguous()       # [nt][kc][T][g][n][8]
+        assert ip.T == T and torch.equal(ip.data.view(-1), want.view(-1))
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,shape", [
+    ("instance", 128, 128, 3, (4, 32, 32, 32)),       # 4-slice tiles (>= one tile per SM)
+    ("group", 128, 128, 3, (2, 8, 16, 16)),           # 2-slice tiles
+    ("instance", 256, 256, 3, (1, 8, 16, 16)),        # 8 chunks, two output-channel tiles
+    ("instance", 64, 64, 3, (1, 6, 8, 8)),            # volume too small for the streaming kernel: 64-row tiles
+    ("instance", 128, 128, (1, 3, 3), (1, 4, 16, 16)),  # 9 taps
+])
+def test_bulk_weight_stream_in_the_tile_kernel(kind, cin, cout, k, shape):
+    """nnd_conv_set_tc_bulk(1): forward and input gradient of conv + norm + ReLU blocks with the weights streamed by cp.async.bulk
+    from the item-order pack -- same arithmetic, same accumulation order as the cp.async variant: results must be IDENTICAL."""
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair(kind, cin, cout, k, 1)
+    g = torch.Generator().manual_seed(66)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    res = {}
+    try:
+        for mode in (True, False):
+            ops.set_tc_bulk(mode)
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            (y, rows) = _trace_kernels(ops, lambda: mine(xm))
+            y.backward(gy.cuda().to(torch.bfloat16))
+            res[mode] = (y.detach().float().cpu(), xm.grad.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop"])
+    finally:
+        ops.set_tc_bulk(False)
+    assert res[True][2] == ["conv_tc_bulk"] and res[False][2] == ["conv_tc"]
+    assert rel_err(res[True][0], yr.detach()) < 5e-3 and rel_err(res[True][1], xr.grad) < 2e-2
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
