@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
-    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 / transposed convs), gather_s2 (tcgen05 stride-2 fprop, up-conv dgrad), tc_bulk (tile kernel weights via cp.async.bulk), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
+    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 / transposed convs), gather_s2 (tcgen05 stride-2 fprop, up-conv dgrad), tc_bulk (tile kernel weights via cp.async.bulk), norm_narrow (4-channel norm backward passes), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
     ap.add_argument("--trace-layers", default=None, metavar="CSV",
                     help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
                          "(kernel chosen, layer geometry, ms, GFLOP per launch) -- maps the step time onto the network")
@@ -199,6 +199,8 @@ def main():
         conv_ops.set_gather_strided_tc(True)
     if "tc_bulk" in args.experimental.split(","):
         conv_ops.set_tc_bulk(True)
+    if "norm_narrow" in args.experimental.split(","):
+        conv_ops.set_norm_bwd_narrow(True)
     arch, anc, patch, bs = make_plan(args.config)
     torch.manual_seed(1234 + rank)
     net = RetinaUNetV001.from_config_plan(None, arch, anc).to(dev)

@@ -169,6 +169,7 @@ int nnd_pack_weights(const float* w, int Cout, int Cin, int T, int transposed, v
 int nnd_norm_finalize(const float* ssum, const float* ssq, const float* gamma, const float* beta, int N, int C, int cpg,
                       long long count, float eps, float* a, float* b, float* mean, float* rstd, cudaStream_t stream);
 int nnd_norm_apply(const void* y, const float* a, const float* b, int N, long long V, int C, int relu, void* z, cudaStream_t stream);
+void nnd_norm_set_bwd_narrow(int enable);             /* opt-in (default 0): 4-channels-per-thread backward passes, not yet measured on a device */
 int nnd_norm_backward(const void* dz, const void* y, const float* a, const float* b, const float* mean, const float* rstd,
                       const float* gamma, int N, long long V, int C, int cpg, int relu, void* dy, float* dgamma, float* dbeta,
                       float* ws /* 5*N*C floats */, cudaStream_t stream);

@@ -252,6 +252,11 @@ def wgrad_strided_tc_enabled() -> bool:
     return _WGRAD_STRIDED_TC
 
 
+def set_norm_bwd_narrow(enable: bool):
+    """Opt-in: norm backward passes with four channels per thread (more resident warps; not yet measured on a device)."""
+    L.lib().nnd_norm_set_bwd_narrow(c_int(1 if enable else 0))
+
+
 def trace_start():
     """Profiling aid: record one row per convolution-family launch (kernel chosen, layer geometry, duration) until `trace_dump`."""
     L.lib().nnd_conv_trace(c_int(1))

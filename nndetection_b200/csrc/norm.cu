@@ -193,6 +193,112 @@ norm_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y,
   }
 }
 
+// ---- narrow variants of the two backward passes (opt-in, nnd_norm_set_bwd_narrow): a thread owns FOUR channels (8-byte loads).
+// The 8-channel kernels above need 127 / 112 registers (coefficients of 8 channels + 8 x 16-byte loads in flight) = two 256-thread
+// CTAs per SM, and were measured at 38 % / 47 % of the HBM peak where norm_apply (62 registers) reaches 88 %; halving the per-thread
+// state doubles the resident warps.  Same per-element arithmetic (dy is bit-identical for identical coefficients); S1 / S2 are summed
+// in a different order.
+__device__ __forceinline__ void unpack4(const uint2& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) { float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint2 pack4(const float* f) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return u;
+}
+
+// grid (chunks, N), block = C4 * rows
+__global__ void __launch_bounds__(256)
+norm_bwd_reduce4_kernel(const uint2* __restrict__ dz, const uint2* __restrict__ y, const float* __restrict__ a,
+                        const float* __restrict__ b, const float* __restrict__ mean, const float* __restrict__ rstd, int V, int C4,
+                        int rows, int vox_per_block, int relu, float* __restrict__ S1, float* __restrict__ S2) {
+  extern __shared__ float sh[];            // [rows][C][2]
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % C4, rr = threadIdx.x / C4;
+  const int C = C4 * 4, c = cc * 4;
+  float av[4], bv[4], mv[4], rv[4], s1[4], s2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    av[j] = a[n * C + c + j]; bv[j] = b[n * C + c + j]; mv[j] = mean[n * C + c + j]; rv[j] = rstd[n * C + c + j];
+    s1[j] = 0.f; s2[j] = 0.f;
+  }
+  const int v0 = blockIdx.x * vox_per_block, v1 = min(v0 + vox_per_block, V);
+  const size_t base = (size_t)n * V * C4 + cc;
+  if (rr < rows) {
+    for (int v = v0 + rr; v < v1; v += 4 * rows) {
+      uint2 iy[4], id[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v + u * rows < v1) { iy[u] = y[base + (size_t)(v + u * rows) * C4]; id[u] = dz[base + (size_t)(v + u * rows) * C4]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (v + u * rows >= v1) break;
+        float fy[4], fd[4];
+        unpack4(iy[u], fy); unpack4(id[u], fd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float pre = fmaf(av[j], fy[j], bv[j]);
+          const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
+          s1[j] += gq;
+          s2[j] += gq * (fy[j] - mv[j]) * rv[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh[(rr * C + c + j) * 2] = s1[j]; sh[(rr * C + c + j) * 2 + 1] = s2[j]; }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int r = 0; r < rows; ++r) { t1 += sh[(r * C + ch) * 2]; t2 += sh[(r * C + ch) * 2 + 1]; }
+    atomicAdd(&S1[n * C + ch], t1);
+    atomicAdd(&S2[n * C + ch], t2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+norm_bwd_apply4_kernel(const uint2* __restrict__ dz, const uint2* __restrict__ y, const float* __restrict__ a,
+                       const float* __restrict__ b, const float* __restrict__ k1, const float* __restrict__ k2,
+                       const float* __restrict__ k3, int V, int C4, int rows, int vox_per_block, int relu, uint2* __restrict__ dy) {
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % C4, rr = threadIdx.x / C4;
+  if (rr >= rows) return;
+  const int C = C4 * 4;
+  float av[4], bv[4], c1[4], c2[4], c3[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = n * C + cc * 4 + j;
+    av[j] = a[o]; bv[j] = b[o]; c1[j] = k1[o]; c2[j] = k2[o]; c3[j] = k3[o];
+  }
+  const int v0 = blockIdx.x * vox_per_block, v1 = min(v0 + vox_per_block, V);
+  const size_t base = (size_t)n * V * C4 + cc;
+  for (int v = v0 + rr; v < v1; v += 4 * rows) {
+    uint2 iy[4], id[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (v + u * rows < v1) { iy[u] = y[base + (size_t)(v + u * rows) * C4]; id[u] = dz[base + (size_t)(v + u * rows) * C4]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v + u * rows >= v1) break;
+      float fy[4], fd[4];
+      unpack4(iy[u], fy); unpack4(id[u], fd);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pre = fmaf(av[j], fy[j], bv[j]);
+        const float gq = (!relu || pre > 0.f) ? fd[j] : 0.f;
+        fd[j] = fmaf(c1[j], gq, fmaf(c2[j], fy[j], c3[j]));
+      }
+      dy[base + (size_t)(v + u * rows) * C4] = pack4(fd);
+    }
+  }
+}
+
+int g_norm_bwd_narrow = 0;
+
 // launch shape shared by the streaming passes: grid (voxel chunks, N), block = rows x C8 threads (<= 256)
 struct StreamShape { int rows, threads, vpb; dim3 grid; };
 static StreamShape stream_shape(int N, long long V, int C8) {
@@ -208,6 +314,9 @@ static StreamShape stream_shape(int N, long long V, int C8) {
 }  // namespace
 
 extern "C" {
+
+// 1: four-channels-per-thread backward passes (see above); default 0 until measured on a B200 (written without one)
+void nnd_norm_set_bwd_narrow(int enable) { g_norm_bwd_narrow = enable; }
 
 // stats [N,C] from the conv epilogue -> a, b, mean, rstd [N,C].  count = voxels per sample.
 int nnd_norm_finalize(const float* ssum, const float* ssq, const float* gamma, const float* beta, int N, int C, int cpg,
@@ -239,6 +348,24 @@ int nnd_norm_backward(const void* dz, const void* y, const float* a, const float
   float* S1 = ws; float* S2 = ws + (size_t)N * C; float* k1 = S2 + (size_t)N * C; float* k2 = k1 + (size_t)N * C;
   float* k3 = k2 + (size_t)N * C;
   NND_CUDA_TRY(cudaMemsetAsync(S1, 0, sizeof(float) * 2 * N * C, st));
+  if (g_norm_bwd_narrow && C <= 1024) {
+    const int C4 = C / 4;
+    int rows = 256 / C4; if (rows < 1) rows = 1;
+    const int threads = rows * C4 > 256 ? C4 : rows * C4;              // C4 <= 256 here (C <= 1024)
+    int vpb = 2048;
+    while (vpb > 64 && (V + vpb - 1) / vpb * N < NND_NUM_SMS * 8) vpb >>= 1;
+    dim3 grid((unsigned)((V + vpb - 1) / vpb), N);
+    const size_t smem = (size_t)rows * C * 2 * sizeof(float);
+    norm_bwd_reduce4_kernel<<<grid, threads, smem, st>>>((const uint2*)dz, (const uint2*)y, a, b, mean, rstd, (int)V, C4, rows, vpb,
+                                                         relu, S1, S2);
+    NND_LAUNCH_CHECK("norm_bwd_reduce4_kernel");
+    norm_bwd_finalize_kernel<<<N, C, 0, st>>>(S1, S2, gamma, mean, rstd, C, cpg, (float)V, k1, k2, k3, dgamma, dbeta);
+    NND_LAUNCH_CHECK("norm_bwd_finalize_kernel");
+    norm_bwd_apply4_kernel<<<grid, threads, 0, st>>>((const uint2*)dz, (const uint2*)y, a, b, k1, k2, k3, (int)V, C4, rows, vpb, relu,
+                                                     (uint2*)dy);
+    NND_LAUNCH_CHECK("norm_bwd_apply4_kernel");
+    return NND_OK;
+  }
   const int C8 = C / 8;
   int rows = 256 / C8; if (rows < 1) rows = 1;
   const int threads = rows * C8;

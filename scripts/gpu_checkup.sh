@@ -14,6 +14,7 @@ NND_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_experimental_gpu.p
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2 > gpurun_out/bench_wgrad_s2.json 2>> gpurun_out/bench.err
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2,gather_s2 > gpurun_out/bench_s2_all.json 2>> gpurun_out/bench.err
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental tc_bulk > gpurun_out/bench_tc_bulk.json 2>> gpurun_out/bench.err
+timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental norm_narrow > gpurun_out/bench_norm_narrow.json 2>> gpurun_out/bench.err
 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -s 2150 -c 900 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --profile > gpurun_out/profile.log 2>&1
 python - <<'PY'
@@ -30,7 +31,7 @@ with open("gpurun_out/layers_summary.txt", "w") as f:
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         f.write(f"{v[0]:7.3f} {100 * v[0] / tot:6.2f} {v[2]:3d} {v[1] / max(v[0], 1e-9):8.1f}  {k[0]:12s} {k[1]:14s} {k[2]:>3s}->{k[3]:<4s} {k[4]:11s} {k[5]:6s} {k[6]}\n")
 PY
-tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; head -c 400 gpurun_out/bench_tc_bulk.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
+tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; head -c 400 gpurun_out/bench_tc_bulk.json; echo; head -c 400 gpurun_out/bench_norm_narrow.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
 # single-layer timings of the strided forms, default kernels vs the opt-in tcgen05 ones
 for args in "32 64 128 4" "64 128 64 4" "128 256 32 4"; do
   for m in fprop wgrad; do

@@ -194,3 +194,29 @@ def test_bulk_weight_stream_in_the_tile_kernel(kind, cin, cout, k, shape):
     assert res[True][2] == ["conv_tc_bulk"] and res[False][2] == ["conv_tc"]
     assert rel_err(res[True][0], yr.detach()) < 5e-3 and rel_err(res[True][1], xr.grad) < 2e-2
     assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+
+
+@pytest.mark.parametrize("kind,c,shape", [("instance", 32, (2, 12, 16, 20)), ("instance", 320, (2, 4, 4, 4)), ("group", 128, (2, 8, 8, 8)),
+                                          ("instance", 64, (1, 5, 7, 9))])
+def test_narrow_norm_backward_passes(kind, c, shape):
+    """nnd_norm_set_bwd_narrow(1): four channels per thread in the two backward streaming passes; same per-element arithmetic, S1 / S2
+    summed in another order -> input gradient and affine gradients agree with the 8-channel kernels to fp32 / bf16 rounding."""
+    from nndetection_b200.arch import conv_ops as ops
+    mine, ref = make_pair(kind, c, c, 3, 1)
+    g = torch.Generator().manual_seed(67)
+    x = q(torch.randn(shape[0], c, *shape[1:], generator=g))
+    gy = q(torch.randn(shape[0], c, *shape[1:], generator=g))
+    res = {}
+    try:
+        for mode in (True, False):
+            ops.set_norm_bwd_narrow(mode)
+            mine.zero_grad(set_to_none=True)
+            xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+            mine(xm).backward(gy.cuda().to(torch.bfloat16))
+            res[mode] = (xm.grad.float().cpu(), mine.norm.weight.grad.cpu().clone(), mine.norm.bias.grad.cpu().clone(),
+                         mine.conv.weight.grad.cpu().clone())
+    finally:
+        ops.set_norm_bwd_narrow(False)
+    assert rel_err(res[True][0], res[False][0]) < 4e-3          # dy is re-rounded to bf16 before the dgrad kernel
+    assert rel_err(res[True][1], res[False][1]) < 1e-4 and rel_err(res[True][2], res[False][2]) < 1e-4
+    assert rel_err(res[True][3], res[False][3]) < 4e-3
