@@ -10,7 +10,14 @@ timeout 600 python -m pytest tests -q -m gpu -rxX 2>&1 | tail -40 > gpurun_out/p
 timeout 420 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 240 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --trace-layers gpurun_out/layers.csv > gpurun_out/bench_trace.json 2>> gpurun_out/bench.err
 # kernels written without a GPU (off by default): their tests in a process of their own, then an A/B bench line
-NND_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_zz_experimental_gpu.py -q 2>&1 | tail -15 > gpurun_out/pytest_experimental.log
+# (one process per test function: an addressing bug in one kernel must not take the others' verdicts with it)
+: > gpurun_out/pytest_experimental.log
+for t in test_strided_wgrad_on_tcgen05 test_transposed_conv_wgrad_on_tcgen05 test_strided_conv_block_forward_on_tcgen05 \
+         test_upconv_input_gradient_on_tcgen05 test_item_order_repack_kernel test_bulk_weight_stream_in_the_tile_kernel \
+         test_narrow_norm_backward_passes; do
+  echo "== $t" >> gpurun_out/pytest_experimental.log
+  NND_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_experimental_gpu.py -q -k "$t" 2>&1 | tail -6 >> gpurun_out/pytest_experimental.log
+done
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2 > gpurun_out/bench_wgrad_s2.json 2>> gpurun_out/bench.err
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental wgrad_s2,gather_s2 > gpurun_out/bench_s2_all.json 2>> gpurun_out/bench.err
 timeout 240 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --experimental tc_bulk > gpurun_out/bench_tc_bulk.json 2>> gpurun_out/bench.err
@@ -31,7 +38,7 @@ with open("gpurun_out/layers_summary.txt", "w") as f:
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         f.write(f"{v[0]:7.3f} {100 * v[0] / tot:6.2f} {v[2]:3d} {v[1] / max(v[0], 1e-9):8.1f}  {k[0]:12s} {k[1]:14s} {k[2]:>3s}->{k[3]:<4s} {k[4]:11s} {k[5]:6s} {k[6]}\n")
 PY
-tail -5 gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; head -c 400 gpurun_out/bench_tc_bulk.json; echo; head -c 400 gpurun_out/bench_norm_narrow.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
+tail -5 gpurun_out/pytest_gpu.log; grep -E '^==|passed|failed|error' gpurun_out/pytest_experimental.log; head -c 400 gpurun_out/bench_wgrad_s2.json; echo; head -c 400 gpurun_out/bench_s2_all.json; echo; head -c 400 gpurun_out/bench_tc_bulk.json; echo; head -c 400 gpurun_out/bench_norm_narrow.json; echo; cat gpurun_out/bench.json | head -c 1500; echo; head -25 gpurun_out/layers_summary.txt
 # single-layer timings of the strided forms, default kernels vs the opt-in tcgen05 ones
 for args in "32 64 128 4" "64 128 64 4" "128 256 32 4"; do
   for m in fprop wgrad; do
