@@ -10,6 +10,12 @@ import torch.multiprocessing as mp
 import torch.nn as nn
 
 
+def _free_port():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
 def _sgd_reference(p, g, mom, lr, momentum, wd, nesterov, first):
     g = g + wd * p
     b = g.clone() if first else momentum * mom + g
@@ -49,7 +55,7 @@ def test_two_rank_gradient_mean_matches_single_process():
     mp.set_start_method("spawn", force=True)
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + os.getpid() % 1000
+    port = _free_port()
     procs = [mp.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
     [p.start() for p in procs]
     [p.join(120) for p in procs]
@@ -176,7 +182,7 @@ def test_gradient_buckets_overlap_gives_the_single_all_reduce_result():
     mp.set_start_method("spawn", force=True)
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() + 7) % 1000
+    port = _free_port()
     procs = [mp.Process(target=_bucket_worker, args=(r, 2, port, ret)) for r in range(2)]
     [p.start() for p in procs]
     [p.join(180) for p in procs]
