@@ -98,3 +98,25 @@ def test_prefix_variant_equals_prefix_of_full_result(n, thr, mk):
     k = min(int(cnt.item()), mk)
     assert k == min(mk, full.numel())
     assert torch.equal(keep[:k].cpu(), full[:k])
+
+
+@pytest.mark.parametrize("n,thr", [(1000, 0.5), (10000, 0.1), (10000, 0.6), (100000, 0.1), (100000, 0.5)])
+def test_ab_against_the_reference_cuda_nms(n, thr):
+    """Head-to-head with the REFERENCE's own kernel (nndet/csrc/cuda/nms.cu:99-221 + ops.cpp, built unmodified except the two-token
+    dispatch fix of nms.cu:172,182 by oracle/build_ref_nms.py into oracle/_ref/): identical keep lists on the SURVEY 8d stress boxes
+    (unique scores, so the sort order is defined), 3-D and 2-D, fp32."""
+    from oracle.build_ref_nms import load
+    ref = load()
+    if ref is None:
+        pytest.skip("oracle/_ref/ref_nms*.so was not built (python oracle/build_ref_nms.py needs /root/reference)")
+    g = torch.Generator().manual_seed(7000 + n)
+    boxes, scores = util.rand_boxes(n, g), util.unique_scores(n, g)
+    b, s = boxes.cuda(), scores.cuda()
+    from nndetection_b200 import _C
+    keep_ref = ref.nms(b, s, thr)
+    keep = _C.nms(b, s, thr)
+    assert keep_ref.dtype == keep.dtype == torch.int64 and keep.is_cuda
+    assert torch.equal(keep, keep_ref), (n, thr, keep.numel(), keep_ref.numel())
+    if n <= 10000:
+        b2 = b[:, :4].contiguous()
+        assert torch.equal(_C.nms(b2, s, thr), ref.nms(b2, s, thr))

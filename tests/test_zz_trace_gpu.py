@@ -1,12 +1,12 @@
 """The per-launch convolution trace (nnd_conv_trace / nnd_conv_trace_dump, a profiling aid behind `bench.py --trace-layers`): one row
 per convolution-family launch of a train step, with the kernel the dispatch chose, the layer geometry and a positive duration.
-Written after the round's GPU budget was spent -> non-strict xfail until its first B200 run (XPASS = it works)."""
+First B200 run: round-1 driver run (XPASS); strict since round 2."""
 import csv
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first device run of the launch trace (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_trace_lists_every_convolution_launch_of_a_train_step(tmp_path):

@@ -251,3 +251,19 @@ def toy_learning_batch(patch, bs, seed):
         tb.append(torch.tensor([[lo[0] + 0.318, lo[1] + 0.328, lo[0] + sd[0] - 0.359, lo[1] + sd[1] - 0.349, lo[2] + 0.338, lo[2] + sd[2] - 0.339]]))
         tc.append(torch.zeros(1, dtype=torch.int64))
     return images, dict(target_boxes=tb, target_classes=tc, target_seg=seg)
+
+
+def oracle_losses_with_indices(orc, images, targets, pos, neg):
+    """The oracle network's four losses on a batch with the sampled anchor indices INJECTED (instead of the oracle's own sampling),
+    plus its ATSS labels and raw outputs: lock-step checks of a device train step (same weights, same batch, same indices)."""
+    from oracle import box_oracle as bo
+    pred, anchors, pseg = orc(images)
+    labels, matched = [], []
+    for a, gb, gc in zip(anchors, targets["target_boxes"], targets["target_classes"]):
+        _, m = bo.atss_match(gb, a, orc.per_level, orc.apos, orc.num_candidates)
+        l, mb = bo.assign_targets(m, gb, gc, a.shape[0])
+        labels.append(l); matched.append(mb)
+    lb, mb, ab = torch.cat(labels), torch.cat(matched), torch.cat(anchors)
+    losses = bo.head_loss(pred["box_logits"], pred["box_deltas"], lb, mb, ab, pos, neg, orc.num_classes)
+    losses.update(bo.seg_loss(pseg["seg_logits"], targets["target_seg"]))
+    return losses, lb, pred
