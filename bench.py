@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
-    ap.add_argument("--experimental", default="", help="comma list of opt-in kernels to A/B: wgrad_s2 (tcgen05 wgrad of stride-2 / transposed convs), gather_s2 (tcgen05 stride-2 fprop, up-conv dgrad), tc_bulk (tile kernel weights via cp.async.bulk), norm_narrow (4-channel norm backward passes), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
+    ap.add_argument("--experimental", default="", help="comma list of A/B switches: mma_s2 (strided / transposed forms on the mma.sync kernels instead of tcgen05), tc_bulk (tile kernel weights via cp.async.bulk: deadlocks, do not use), norm_narrow (4-channel norm backward passes), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
     ap.add_argument("--trace-layers", default=None, metavar="CSV",
                     help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
                          "(kernel chosen, layer geometry, ms, GFLOP per launch) -- maps the step time onto the network")
@@ -193,10 +193,9 @@ def main():
     lib.nnd_launch_count.restype = __import__("ctypes").c_ulonglong
     if args.igemm_only:
         conv_ops.set_tensor_path(False)
-    if "wgrad_s2" in args.experimental.split(","):
-        conv_ops.set_wgrad_strided_tc(True)
-    if "gather_s2" in args.experimental.split(","):
-        conv_ops.set_gather_strided_tc(True)
+    if "mma_s2" in args.experimental.split(","):             # A/B: strided / transposed forms back on the mma.sync kernels (round-1 default)
+        conv_ops.set_wgrad_strided_tc(False)
+        conv_ops.set_gather_strided_tc(False)
     if "tc_bulk" in args.experimental.split(","):
         conv_ops.set_tc_bulk(True)
     if "norm_narrow" in args.experimental.split(","):
@@ -322,6 +321,10 @@ def main():
             except Exception as e:                       # a comparator, never allowed to cost the result line
                 out["gpu_baseline"] = {"value": None, "unit": UNIT, "kind": "stock PyTorch/cuDNN modules", "sample": f"failed: {e!r}"}
             try:
+                out["nms_vs_reference_cuda"] = ref_nms_rates(dev)
+            except Exception as e:
+                out["nms_vs_reference_cuda"] = {"error": repr(e)}
+            try:
                 out["cpu_baseline"] = cpu_baseline()
             except Exception as e:                       # never lose the GPU line to a host-side problem
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
@@ -363,42 +366,79 @@ def conv_roofline(net, dev, arch, patch, bs):
     kname = {2: "conv_tcs_kernel (tcgen05, streaming z-window N=96 MMAs)", 1: "conv_tc_kernel (tcgen05 tile kernel)"}.get(used, "conv_igemm_kernel<32> (mma.sync)")
     # DRAM traffic of this launch from the committed `ncu --set full` capture (profiles/r01_ncu_conv_tcs32_summary.txt):
     # dram__bytes_read.sum 545.0 MB + dram__bytes_write.sum 483.8 MB -- equals the algorithmic bytes (no re-reads)
-    traffic = 544.989952e6 + 483.824384e6 if used == 2 else None
+    luna_shape = used == 2 and tuple(patch) == (128, 128, 128) and bs == 4
+    traffic = 544.989952e6 + 483.824384e6 if luna_shape else None       # the capture is of THIS shape only; other configs: null
     return {"bound": "tensor", "kernel": kname,
-            "layer": f"encoder.stage0.conv2 {cin}->{cout} 3x3x3 @ {patch[0]}^3 x batch {bs}",
+            "layer": f"encoder.stage0.conv2 {cin}->{cout} 3x3x3 @ {patch[0]}x{patch[1]}x{patch[2]} x batch {bs}",
             "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst, "peak_kind": kind + " burst bf16 cuBLAS",
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": traffic,
-            "traffic_source": "profiles/r01_ncu_conv_tcs32_summary.txt (ncu --set full, same layer and shape)"}
+            "traffic_source": "profiles/r01_ncu_conv_tcs32_summary.txt (ncu --set full, same layer and shape)" if luna_shape else None}
+
+
+def _nms_stress(n, dev):
+    g = torch.Generator().manual_seed(7)
+    c = torch.rand(n, 3, generator=g) * 160
+    h = torch.rand(n, 3, generator=g) * 20 + 2
+    boxes = torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1], c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], 1).to(dev)
+    scores = ((torch.randperm(n, generator=g).float() + 0.5) / n).to(dev)
+    return boxes, scores
+
+
+def _time_nms(fn, boxes, scores, thr, it):
+    for _ in range(2):
+        keep = fn(boxes, scores, thr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(it):
+        keep = fn(boxes, scores, thr)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / it, keep
+
+
+def ref_nms_rates(dev):
+    """Head-to-head with the REFERENCE's own CUDA NMS (nndet/csrc/cuda/nms.cu:99-221, built by oracle/build_ref_nms.py into
+    oracle/_ref/ -- a comparator, like `gpu_baseline`): one call each on the same stress boxes, keep lists compared."""
+    from oracle.build_ref_nms import load
+    from nndetection_b200 import _C
+    ref = load()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/ref_nms*.so not built"}
+    res = {"kind": "reference nndet._C.nms (nms.cu + ops.cpp, two-token dispatch fix), same GPU, same boxes, thr 0.1"}
+    for n in (1_000, 10_000, 100_000):
+        boxes, scores = _nms_stress(n, dev)
+        it = 10 if n <= 10_000 else 3
+        ms_ref, keep_ref = _time_nms(ref.nms, boxes, scores, 0.1, it)
+        ms, keep = _time_nms(_C.nms, boxes, scores, 0.1, it)
+        res[f"n{n}"] = {"ref_ms": ms_ref, "ms": ms, "speedup": ms_ref / ms, "ref_boxes_per_s": n / (ms_ref / 1e3),
+                        "boxes_per_s": n / (ms / 1e3), "keep_equal": bool(torch.equal(keep, keep_ref)), "kept": int(keep.numel())}
+    return res
+
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)
 
 
 def nms_rates(dev):
     """BASELINE.json's second metric: 3-D NMS boxes/s = N / time of ONE nndet._C.nms call (sort included), SURVEY 8d stress
     boxes (centres U[0,160)^3, half sizes U[2,22), unique scores), thr 0.1; bytes = 28N + 8N + 8 N ceil(N/64) (upper
-    triangle written once, read once) + 8K; pair tests = N (N-1) / 2."""
+    triangle written once, read once) + 8K; pair tests = N (N-1) / 2.  `roofline`: the all-pairs phase is fp32-ALU-bound
+    (~22 flop per pair test, 176 flop per mask byte), so the fraction is pair tests x 22 / nominal fp32 peak; the
+    HBM fraction of the algorithmic bytes is reported beside it (the north star's 70 % HBM target is the wrong roof for N >= 2 k)."""
     from nndetection_b200 import _C
     res = {}
-    for n in (10_000, 100_000):
-        g = torch.Generator().manual_seed(7)
-        c = torch.rand(n, 3, generator=g) * 160
-        h = torch.rand(n, 3, generator=g) * 20 + 2
-        boxes = torch.stack([c[:, 0] - h[:, 0], c[:, 1] - h[:, 1], c[:, 0] + h[:, 0], c[:, 1] + h[:, 1], c[:, 2] - h[:, 2], c[:, 2] + h[:, 2]], 1).to(dev)
-        scores = ((torch.randperm(n, generator=g).float() + 0.5) / n).to(dev)
-        for _ in range(2):
-            keep = _C.nms(boxes, scores, 0.1)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        it = 10 if n <= 10_000 else 3
-        e0.record()
-        for _ in range(it):
-            keep = _C.nms(boxes, scores, 0.1)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / it
+    for n in (1_000, 10_000, 100_000):
+        boxes, scores = _nms_stress(n, dev)
+        ms, keep = _time_nms(_C.nms, boxes, scores, 0.1, 10 if n <= 10_000 else 3)
         k = int(keep.numel())
         byt = 36.0 * n + 8.0 * n * ((n + 63) // 64) + 8.0 * k
+        pairs = 0.5 * n * (n - 1) / (ms / 1e3)
         res[f"n{n}"] = {"ms": ms, "boxes_per_s": n / (ms / 1e3), "kept": k, "algorithmic_GB_per_s": byt / (ms / 1e3) / 1e9,
-                        "pair_tests_per_s": 0.5 * n * (n - 1) / (ms / 1e3)}
+                        "pair_tests_per_s": pairs,
+                        "roofline": {"bound": "fp32 alu", "achieved": pairs * 22 / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                     "frac": pairs * 22 / 1e12 / FP32_PEAK_TFLOPS, "peak_kind": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                                     "hbm_frac_of_measured": byt / (ms / 1e3) / 1e9 / peaks()[0]}}
     return res
 
 

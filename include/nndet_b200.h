@@ -188,6 +188,10 @@ int nnd_seg_conv_bwd(const void* x, int C, const float* w, const float* dlogits,
  *      nndet/ptmodule/retinaunet/base.py:300-336; elements >= n_decay get no weight decay (norm params). */
 int nnd_sgd_step(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
                  int nesterov, int first_step, float grad_scale, cudaStream_t stream);
+/* same, leaving n_skip [lo, hi) element ranges (device int64 pairs) untouched: parameters that never receive a gradient, which
+ * torch.optim.SGD skips (`p.grad is None`) -- no weight decay, no momentum for them. */
+int nnd_sgd_step_skip(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
+                      int nesterov, int first_step, float grad_scale, const long long* skip, int n_skip, cudaStream_t stream);
 int nnd_pad_cast_f32_bf16(const float* src, int N, long long rows, int C, long long src_n_stride, const float* mul, void* dst,
                           int Cpad, cudaStream_t stream);
 int nnd_channel_sum(const void* src, int is_bf16, long long rows, int C, long long stride, float scale, float* out, cudaStream_t stream);

@@ -148,6 +148,7 @@ class _ConvBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         layer, plan, N, V = ctx.layer, ctx.plan, ctx.N, ctx.V
+        layer._nnd_grad_seen = True           # training.FlatParameters.find_unused: this layer's parameters receive gradients
         conv: ConvParams = layer.conv
         cin, cout = conv.in_channels, conv.out_channels
         has_norm = layer.norm is not None
@@ -288,7 +289,7 @@ class BaseConvNormAct(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_plans", "_packed", "_packed_key", "_items"):
+            if k in ("_plans", "_packed", "_packed_key", "_items", "_nnd_grad_seen"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._plans, new._packed, new._packed_key = {}, None, None

@@ -156,7 +156,7 @@ _TC_BULK = False
 
 
 def set_tc_bulk(enable: bool):
-    """Opt-in: the tile kernel's weight stream through cp.async.bulk on item-order packs (not yet validated on a device; default off)."""
+    """Do not enable: this variant of the tile kernel (weights via cp.async.bulk on item-order packs) deadlocks on the device."""
     global _TC_BULK
     L.lib().nnd_conv_set_tc_bulk(c_int(1 if enable else 0))
     _TC_BULK = bool(enable)
@@ -231,20 +231,19 @@ def set_stream_path(mode: int = 1, issuers: int = 2):
 
 
 
-_WGRAD_STRIDED_TC = False
+_WGRAD_STRIDED_TC = True        # default since round 2 (validated on a B200); the C side has the same default
 
 
 def set_wgrad_strided_tc(enable: bool):
-    """Opt-in: de-interleaved tcgen05 weight gradient for stride-2 convolutions and kernel == stride transposed convolutions
-    (not yet validated on a device; default off)."""
+    """De-interleaved tcgen05 weight gradient for stride-2 convolutions and kernel == stride transposed convolutions (default on;
+    False = the mma.sync kernels, for A/B)."""
     global _WGRAD_STRIDED_TC
     L.lib().nnd_conv_set_wgrad_strided_tc(c_int(1 if enable else 0))
     _WGRAD_STRIDED_TC = bool(enable)
 
 
 def set_gather_strided_tc(enable: bool):
-    """Opt-in: de-interleaved-halo tcgen05 kernel for stride-2 convolutions and the dgrad of up-convolutions (not yet validated on
-    a device; default off)."""
+    """De-interleaved-halo tcgen05 kernel for stride-2 convolutions and the dgrad of up-convolutions (default on; False = mma.sync)."""
     L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
 
 

@@ -275,6 +275,7 @@ class _HeadOutFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_logits, d_deltas):
         head = ctx.head
+        head._nnd_grad_seen = True
         N, A, C, apos, sps, vox, offs, cin, plans = ctx.meta
         nl, ns = head.num_levels, head.n_scales
         saved = ctx.saved_tensors
@@ -380,7 +381,7 @@ class DetectionHeadHNMNative(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_packed", "_packed_key", "_plans"):
+            if k in ("_packed", "_packed_key", "_plans", "_nnd_grad_seen"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._packed, new._packed_key, new._plans = None, None, {}
@@ -390,7 +391,8 @@ class DetectionHeadHNMNative(nn.Module):
 # ------------------------------------------------------------------------------------------------ segmenter
 class _SegConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, owner=None):
+        ctx.owner = owner
         x = ops.as_cl(x)
         N, C = x.shape[0], x.shape[1]
         sp = tuple(x.shape[2:])
@@ -404,6 +406,8 @@ class _SegConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         x, w = ctx.saved_tensors
+        if ctx.owner is not None:
+            ctx.owner._nnd_grad_seen = True
         N, C = x.shape[0], x.shape[1]
         sp = tuple(x.shape[2:])
         total = N * sp[0] * sp[1] * sp[2]
@@ -413,7 +417,7 @@ class _SegConvFn(torch.autograd.Function):
         db = torch.zeros(2, dtype=torch.float32, device=x.device)
         L.check(L.lib().nnd_seg_conv_bwd(L.ptr(x), c_int(C), L.ptr(w.detach()), L.ptr(dl), c_longlong(total), L.ptr(dx),
                                          L.ptr(dw), L.ptr(db), L.stream_ptr()), "nnd_seg_conv_bwd")
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class _SegLossFn(torch.autograd.Function):
@@ -462,7 +466,7 @@ class DiCESegmenterFgBg(nn.Module):
 
     def forward(self, x: List[Tensor]) -> Dict[str, Tensor]:
         c = self.conv_out.conv
-        return {"seg_logits": _SegConvFn.apply(x[0], c.weight.view(2, -1), c.bias)}
+        return {"seg_logits": _SegConvFn.apply(x[0], c.weight.view(2, -1), c.bias, self)}
 
     def compute_loss(self, pred_seg: Dict[str, Tensor], target: Tensor) -> Dict[str, Tensor]:
         ce, dice = _SegLossFn.apply(pred_seg["seg_logits"], target, self.alpha, self.smooth)

@@ -59,8 +59,8 @@ int parse_geom(const int* a, ConvGeom& g) {
 int g_force_igemm = 0;
 int g_wgrad_tc = 1;
 int g_stream = 1;
-int g_wgrad_strided = 0;
-int g_gather_strided = 0;
+int g_wgrad_strided = 1;      // validated on a B200 in round 2 (tests/test_strided_tcgen05_gpu.py), default since
+int g_gather_strided = 1;
 int g_tc_bulk = 0;
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
@@ -103,13 +103,13 @@ void nnd_conv_set_tensor_path(int enable_tcgen05) { g_force_igemm = !enable_tcge
 // volumes too small to fill the grid (tests)
 void nnd_conv_set_wgrad_tc(int enable) { g_wgrad_tc = enable; }
 // 1: stride-2 convolutions take the de-interleaved tcgen05 wgrad (conv_wgrad_tc.cu, SW = 2) instead of the mma.sync kernels.
-// Default 0 until the variant has been validated on a B200 (it was written without one); tests/test_zz_experimental_gpu.py.
+// Default 1 since round 2 (validated on a B200: tests/test_strided_tcgen05_gpu.py; luna step 32.6 -> 30.8 ms with both switches); 0 = A/B.
 void nnd_conv_set_wgrad_strided_tc(int enable) { g_wgrad_strided = enable; }
 // 1: stride-2 gathers (3x3x3 stride-2 convolutions, dgrad of up-convolutions) take the de-interleaved-halo tcgen05 tile kernel
-// (conv_tc.cu, S2 = 1) instead of the mma.sync kernel.  Default 0 until validated on a B200 (written without one).
+// (conv_tc.cu, S2 = 1) instead of the mma.sync kernel.  Default 1 since round 2 (see above).
 void nnd_conv_set_gather_strided_tc(int enable) { g_gather_strided = enable; }
 // 1: launches that bring an item-order weight pack (nnd_conv_gather_bf16_items) stream it with cp.async.bulk (conv_tc.cu, BULK = 1).
-// Default 0 until validated on a B200 (written without one).
+// Default 0: the variant DEADLOCKS on the device (round-2 run: its test hit the 200 s timeout) -- kept only as a record, do not enable.
 void nnd_conv_set_tc_bulk(int enable) { g_tc_bulk = enable; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.

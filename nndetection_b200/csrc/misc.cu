@@ -45,9 +45,12 @@ __global__ void repack_items_kernel(const uint4* __restrict__ src, int T, int ro
 // (norm parameters, nndet/training/optimizer/utils.py).  first_step: momentum buffer initialised with the gradient.
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, long long n,
                            long long n_decay, float lr, float momentum, float wd, int nesterov, int first_step,
-                           float grad_scale) {
+                           float grad_scale, const long long* __restrict__ skip, int n_skip) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // parameters that never receive a gradient (torch.optim.SGD skips `p.grad is None`: no decay, no momentum): [lo, hi) element ranges
+  for (int k = 0; k < n_skip; ++k)
+    if (i >= skip[2 * k] && i < skip[2 * k + 1]) return;
   float gr = g[i] * grad_scale;
   const float pv = p[i];
   if (i < n_decay) gr = fmaf(wd, pv, gr);
@@ -170,12 +173,19 @@ int nnd_repack_items_bf16(const void* src, int T, int rows_pad, int K, int n_til
   return NND_OK;
 }
 
-int nnd_sgd_step(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
-                 int nesterov, int first_step, float grad_scale, cudaStream_t st) {
+// skip: device array of n_skip [lo, hi) element ranges left untouched (parameters without a gradient), or NULL / 0
+int nnd_sgd_step_skip(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
+                      int nesterov, int first_step, float grad_scale, const long long* skip, int n_skip, cudaStream_t st) {
   if (n <= 0) return NND_OK;
-  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, mom, n, n_decay, lr, momentum, wd, nesterov, first_step, grad_scale);
+  if (n_skip < 0 || (n_skip > 0 && !skip)) return NND_ERR_ARG;
+  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, g, mom, n, n_decay, lr, momentum, wd, nesterov, first_step, grad_scale, skip, n_skip);
   NND_LAUNCH_CHECK("sgd_kernel");
   return NND_OK;
+}
+
+int nnd_sgd_step(float* p, const float* g, float* mom, long long n, long long n_decay, float lr, float momentum, float wd,
+                 int nesterov, int first_step, float grad_scale, cudaStream_t st) {
+  return nnd_sgd_step_skip(p, g, mom, n, n_decay, lr, momentum, wd, nesterov, first_step, grad_scale, nullptr, 0, st);
 }
 
 int nnd_pad_cast_f32_bf16(const float* src, int N, long long rows, int C, long long src_n_stride, const float* mul, void* dst,

@@ -116,13 +116,14 @@ __device__ void pick_by_hash(const int* __restrict__ list, int n, int k, unsigne
 }
 
 __global__ void __launch_bounds__(1024)
-hnm_pick_kernel(const int* __restrict__ counts, const int* __restrict__ pos_list, const int* __restrict__ pool_list,
+hnm_pick_kernel(const int* __restrict__ counts, const int* __restrict__ pos_list, int pos_cap, const int* __restrict__ pool_list,
                 unsigned int seed, long long* __restrict__ pos_out, long long* __restrict__ neg_out) {
   __shared__ int s_sel[MAX_SEL];
   __shared__ unsigned int hist[256];
   __shared__ int ctl[4];
   __shared__ int s_cnt;
-  pick_by_hash(pos_list, counts[0], counts[2], seed, 1u, pos_out, s_sel, hist, ctl, &s_cnt);
+  // counts[0] keeps counting past the list's capacity (counts[6] flags it): never read beyond what hnm_count_kernel stored
+  pick_by_hash(pos_list, min(counts[0], pos_cap), counts[2], seed, 1u, pos_out, s_sel, hist, ctl, &s_cnt);
   pick_by_hash(pool_list, counts[4], counts[3], seed, 2u, neg_out, s_sel, hist, ctl, &s_cnt);
 }
 
@@ -307,7 +308,7 @@ int nnd_hnm_sample(const float* labels, const float* fg_probs, long long n, int 
   }
   pool_collect_kernel<<<blocks, 256, 0, st>>>(labels, fg_probs, n, state, counts_out, pool_list);
   NND_LAUNCH_CHECK("pool_collect_kernel");
-  hnm_pick_kernel<<<1, 1024, 0, st>>>(counts_out, pos_list, pool_list, seed, pos_out, neg_out);
+  hnm_pick_kernel<<<1, 1024, 0, st>>>(counts_out, pos_list, pos_cap, pool_list, seed, pos_out, neg_out);
   NND_LAUNCH_CHECK("hnm_pick_kernel");
   return NND_OK;
 }

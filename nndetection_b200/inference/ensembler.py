@@ -271,15 +271,37 @@ class BoxEnsemblerSelective:
         from pathlib import Path
         return [c.stem.rsplit(f"_{cls.ID}", 1)[0] for c in Path(base_dir).glob(f"*_{cls.ID}.pt")]
 
+    def restore_prediction(self, boxes: Tensor) -> Tensor:
+        """detection.py:254-274 + nndet/inference/restore.py:30-66 (`restore_detection`) + core/boxes/ops.py:330-374: boxes from the
+        preprocessed space into the original image space -- axes permuted by `transpose_backward`, scaled by resampled / original
+        spacing, shifted by the crop offset.  At most `ensemble_topk` boxes: the arithmetic is the reference's numpy float64 on the
+        host (one small D2H copy), the result returns to the boxes' device and dtype."""
+        import numpy as np
+        pr = self.properties
+        tb = [int(d) for d in pr["transpose_backward"]]
+        b = boxes.detach().cpu().numpy()
+        if 2 * len(tb) != b.shape[1]:
+            raise TypeError(f"Need same number of dimensions, found dims {tb} but boxes with shape {b.shape}")
+        pairs = [[0, 2], [1, 3], [4, 5]]
+        axis = [pairs[tb[0]][0], pairs[tb[1]][0], pairs[tb[0]][1], pairs[tb[1]][1]]
+        for d in tb[2:]:
+            axis.extend(pairs[d])
+        b = b[:, axis]
+        expand = [0, 1, 0, 1] + ([2, 2] if len(tb) == 3 else [])
+        scaling = np.asarray(pr["spacing_after_resampling"])[tb] / np.asarray(pr["original_spacing"])
+        offset = np.asarray([i[0] for i in pr["crop_bbox"]])
+        b = b * scaling[None][:, expand] + offset[None][:, expand]
+        return torch.from_numpy(b).to(device=boxes.device, dtype=boxes.dtype)
+
     @torch.no_grad()
     def get_case_result(self, restore: bool = False, names: Optional[Sequence[Hashable]] = None) -> Dict[str, Any]:
         """detection.py:422-474."""
-        if restore:
-            raise NotImplementedError("restore=True needs nndet.inference.restore (ITK-side resampling): out of scope")
         names = list(self.model_results.keys()) if names is None else names
         per_model = [self.process_model(name) for name in names]
         boxes, probs, labels = self.process_ensemble(boxes=[m[0] for m in per_model], probs=[m[1] for m in per_model],
                                                      labels=[m[2] for m in per_model], weights=[m[3] for m in per_model])
+        if restore:
+            boxes = self.restore_prediction(boxes)
         out = {"pred_boxes": boxes, "pred_scores": probs, "pred_labels": labels, "restore": restore}
         for k in ("original_size_of_raw_data", "itk_origin", "itk_spacing", "itk_direction"):
             if k in self.properties:

@@ -46,9 +46,57 @@ class FlatParameters:
             p._nnd_direct_grad = True                             # ... and the conv / norm kernels add straight into it
             off += k
         self.first_step = True
+        self.skip, self.n_skip, self.unused = None, 0, None
+        ids = {id(p): n for n, p in model.named_parameters()}
+        self.names = [(ids.get(id(p), "?"), p) for p in self.params]
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def find_unused(self, model: nn.Module):
+        """Parameters that receive no gradient at all (e.g. decoder `out.P1` under the LUNA plan: its output feeds neither head nor
+        segmenter) keep `grad is None` in the reference, and torch.optim.SGD skips them -- no weight decay, no momentum.  Here every
+        parameter owns a slice of the flat gradient buffer, so "no gradient" is read off the layers instead: each layer's backward
+        function marks the layer (`_nnd_grad_seen`, arch/conv.py / arch/net.py) when autograd runs it.  After the first backward pass the
+        parameters of layers of THIS package that were never marked are handed to the optimizer kernel as element ranges to leave
+        alone (the graph is static).  Parameters of foreign modules are always updated."""
+        from .arch.conv import BaseConvNormAct
+        from .arch.net import DetectionHeadHNMNative, DiCESegmenterFgBg
+        unused = set()
+        for m in model.modules():
+            if getattr(m, "_nnd_grad_seen", False):
+                continue
+            if isinstance(m, BaseConvNormAct):
+                owned = list(m.conv.parameters()) + (list(m.norm.parameters()) if m.norm is not None else [])
+            elif isinstance(m, DetectionHeadHNMNative):
+                owned = list(m.classifier.conv_out.parameters()) + list(m.regressor.conv_out.parameters()) + \
+                    ([s.scale for s in m.regressor.scales] if m.n_scales else [])
+            elif isinstance(m, DiCESegmenterFgBg):
+                owned = list(m.conv_out.parameters())
+            else:
+                continue
+            unused.update(id(p) for p in owned)
+        ranges, off = [], 0
+        for p in self.params:
+            k = p.numel()
+            if id(p) in unused:
+                if ranges and ranges[-1][1] == off:
+                    ranges[-1][1] = off + k
+                else:
+                    ranges.append([off, off + k])
+            off += k
+        self.unused = [n for n, p in self.names if id(p) in unused]
+        self.n_skip = len(ranges)
+        self.skip = torch.tensor(ranges, dtype=torch.int64, device=self.flat.device).reshape(-1) if ranges else None
+
+    def check_homed(self):
+        """`model.to()` / `.float()` / `.cuda()` after construction re-home `p.data`: the optimizer kernel would then update a buffer the
+        model no longer reads.  One pointer comparison per parameter (host only), once per step."""
+        base, end = self.flat.data_ptr(), self.flat.data_ptr() + 4 * self.n
+        for p in self.params:
+            if not (base <= p.data_ptr() < end) or p.grad is None or not (self.grad.data_ptr() <= p.grad.data_ptr() < self.grad.data_ptr() + 4 * self.n):
+                raise RuntimeError("a parameter (or its .grad) no longer lives in the Trainer's flat buffer: build the Trainer after "
+                                   "the last model.to()/.float()/.cuda(), and do not replace .grad tensors (zero them in place)")
 
 
 class GradientBuckets:
@@ -175,11 +223,15 @@ class Trainer:
 
     def optimizer_step(self):
         fp = self.fp
+        fp.check_homed()
         lr = poly_lr(self.step_idx, **self.cfg)
-        L.check(L.lib().nnd_sgd_step(L.ptr(fp.flat), L.ptr(fp.grad), L.ptr(fp.mom), c_longlong(fp.n), c_longlong(fp.n_decay),
-                                     c_float(lr), c_float(self.momentum), c_float(self.weight_decay),
-                                     c_int(1 if self.nesterov else 0), c_int(1 if fp.first_step else 0),
-                                     c_float(1.0 / self.world), L.stream_ptr()), "nnd_sgd_step")
+        if fp.first_step:
+            fp.find_unused(self.model)
+        L.check(L.lib().nnd_sgd_step_skip(L.ptr(fp.flat), L.ptr(fp.grad), L.ptr(fp.mom), c_longlong(fp.n), c_longlong(fp.n_decay),
+                                          c_float(lr), c_float(self.momentum), c_float(self.weight_decay),
+                                          c_int(1 if self.nesterov else 0), c_int(1 if fp.first_step else 0),
+                                          c_float(1.0 / self.world), L.ptr(fp.skip), c_int(fp.n_skip), L.stream_ptr()),
+                "nnd_sgd_step_skip")
         fp.first_step = False
         self.step_idx += 1
         bump_weights_epoch()              # packed bf16 weight copies are refreshed lazily by the layers

@@ -4,7 +4,7 @@ up-convolutions / output convs, shared head convs per decoder level), every laun
 the library's dry-run dispatch queries (`nnd_conv_gather_dispatch`, `nnd_conv_wgrad_dispatch`: the same `*_supported` predicates the
 real dispatch uses).  The image layer (Cin <= 4) and the 1x1x1 segmentation conv have kernels of their own and are listed as such.
 
-    python scripts/dispatch_report.py [config] [--experimental]      # config: luna (default) | adam | lidc | infer160 | toy | tiny
+    python scripts/dispatch_report.py [config] [--mma-s2]      # config: luna (default) | adam | lidc | infer160 | toy | tiny
 """
 import os
 import sys
@@ -13,9 +13,9 @@ from ctypes import c_int, c_longlong
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2 (opt-in)"}
+GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2"}
 WGRAD = {0: "wgrad generic (mma.sync)", 1: "wgrad halo (mma.sync)", 2: "conv_wgrad_tc", 3: "conv_wgrad_tc32", 4: "conv_wgrad_tcn",
-         5: "conv_wgrad_tc SW=2 (opt-in)"}
+         5: "conv_wgrad_tc SW=2"}
 
 
 def pad32(c):
@@ -56,7 +56,7 @@ def layers_of(arch, patch, bs):
     return out
 
 
-def report(config="luna", experimental=False, quiet=False):
+def report(config="luna", experimental=True, quiet=False):      # experimental=False: strided forms on mma.sync (round-1 default, A/B)
     from nndetection_b200 import _lib as L
     from nndetection_b200.arch.conv_ops import ConvPlan
     from nndetection_b200.configs import make_plan
@@ -102,12 +102,12 @@ def report(config="luna", experimental=False, quiet=False):
         if not name.startswith("encoder.stage0.conv1"):
             add("dgrad", d, gf)
         rows.append((name, cin, cout, in_sp, s, f, d, w, gf))
-    lib.nnd_conv_set_gather_strided_tc(c_int(0))
-    lib.nnd_conv_set_wgrad_strided_tc(c_int(0))
+    lib.nnd_conv_set_gather_strided_tc(c_int(1))      # back to the defaults
+    lib.nnd_conv_set_wgrad_strided_tc(c_int(1))
     tot = sum(totals.values())
     tensor = sum(v for k, v in totals.items() if "mma.sync" not in k)
     if not quiet:
-        print(f"# {config}: batch {bs} x {patch}, opt-in strided kernels {'ON' if experimental else 'off'}")
+        print(f"# {config}: batch {bs} x {patch}, strided / transposed forms on {'tcgen05 (default)' if experimental else 'mma.sync (A/B)'}")
         print(f"{'layer':34s} {'Cin':>4s} {'Cout':>4s} {'input':>14s} {'stride':>8s}  {'GFLOP':>7s}  fprop | dgrad | wgrad")
         for name, cin, cout, in_sp, s, f, d, w, gf in rows:
             print(f"{name:34s} {cin:4d} {cout:4d} {'x'.join(map(str, in_sp)):>14s} {'x'.join(map(str, s)):>8s}  {gf:7.1f}  {f} | {d} | {w}")
@@ -120,4 +120,4 @@ def report(config="luna", experimental=False, quiet=False):
 
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    report(args[0] if args else "luna", "--experimental" in sys.argv)
+    report(args[0] if args else "luna", "--mma-s2" not in sys.argv)

@@ -538,6 +538,43 @@ def gen_sweeper():
 
 
 # ------------------------------------------------------------------------------------------ learning-rate schedule
+def gen_restore():
+    """`restore_detection` (nndet/inference/restore.py:30-66, with permute_boxes / expand_to_boxes of core/boxes/ops.py:330-374) executed
+    from its file (its module-level imports of loguru / the ITK-side resampling helpers are stubbed: the function uses neither), as
+    `BoxEnsembler.restore_prediction` calls it (ensembler/detection.py:254-274): float32 boxes in, float64 numpy arithmetic, float32 out."""
+    import importlib, types
+    root = ref_import.REF_ROOT
+    if "nndet.inference" not in sys.modules or not hasattr(sys.modules["nndet.inference"], "__path__"):
+        pkg = types.ModuleType("nndet.inference"); pkg.__path__ = [os.path.join(root, "nndet/inference")]; sys.modules["nndet.inference"] = pkg
+    if "loguru" not in sys.modules:
+        lg = types.ModuleType("loguru"); lg.logger = types.SimpleNamespace(info=print, warning=print, error=print); sys.modules["loguru"] = lg
+    if "nndet.preprocessing.resampling" not in sys.modules:
+        pp = sys.modules.setdefault("nndet.preprocessing", types.ModuleType("nndet.preprocessing"))
+        rs = types.ModuleType("nndet.preprocessing.resampling")
+        rs.resample_data_or_seg = rs.get_do_separate_z = rs.get_lowres_axis = None
+        sys.modules["nndet.preprocessing.resampling"] = rs; pp.resampling = rs
+    sys.modules.pop("nndet.inference.restore", None)
+    restore = importlib.import_module("nndet.inference.restore")
+    out = {}
+    cases = [((0, 1, 2), (1.0, 1.0, 1.0), (1.0, 1.0, 1.0), [(0, 10), (0, 20), (0, 30)]),
+             ((2, 0, 1), (2.5, 0.7, 0.7), (0.8, 1.25, 0.9), [(3, 90), (11, 200), (7, 150)]),
+             ((1, 2, 0), (0.5, 0.5, 3.0), (1.0, 1.0, 1.0), [(0, 64), (5, 69), (17, 81)]),
+             ((2, 1, 0), (1.37, 0.91, 0.66), (1.5, 0.75, 0.75), [(21, 50), (0, 40), (9, 99)])]
+    g = torch.Generator().manual_seed(77)
+    for i, (tb, osp, rsp, crop) in enumerate(cases):
+        boxes = rand_boxes(40 + i, g).float()
+        props = dict(transpose_backward=list(tb), original_spacing=np.asarray(osp), spacing_after_resampling=np.asarray(rsp), crop_bbox=crop)
+        ref = restore.restore_detection(boxes.numpy(), **props)
+        res = torch.from_numpy(ref).to(dtype=boxes.dtype)
+        out[f"boxes{i}"] = boxes.numpy(); out[f"restored{i}"] = res.numpy()
+        out[f"tb{i}"] = np.asarray(tb); out[f"osp{i}"] = np.asarray(osp); out[f"rsp{i}"] = np.asarray(rsp); out[f"crop{i}"] = np.asarray(crop)
+        from nndetection_b200.inference.ensembler import BoxEnsemblerSelective
+        mine = BoxEnsemblerSelective.from_case({"data": torch.zeros(1, 8, 8, 8)}, properties=props)
+        assert torch.equal(mine.restore_prediction(boxes), res), i
+    out["n_cases"] = np.asarray(len(cases))
+    save("restore", **out)
+
+
 def gen_lr():
     """LinearWarmupPolyLR (nndet/training/learning_rate.py:126-183) executed: the lr the optimizer holds at every step."""
     import importlib.util
@@ -826,7 +863,7 @@ def gen_model(name="tiny", seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "helper", "sweeper", "lr", "model"]
+    which = sys.argv[1:] or ["pairwise", "anchors", "atss", "sampler", "coder", "nms", "wbc", "transforms", "ensembler", "predictor", "helper", "sweeper", "restore", "lr", "model"]
     for w in which:
         print("==", w)
         globals()["gen_" + w]()

@@ -22,9 +22,9 @@ if os.environ.get("NND_TC_RING"):
     from ctypes import c_int as _ci
     L2.lib().nnd_conv_set_tc_ring(_ci(int(os.environ["NND_TC_RING"])))
 stride = int(os.environ.get("NND_STRIDE", "1"))
-if os.environ.get("NND_S2"):
-    ops.set_gather_strided_tc(True)
-    ops.set_wgrad_strided_tc(True)
+if os.environ.get("NND_S2") == "0":          # A/B: strided forms on the mma.sync kernels
+    ops.set_gather_strided_tc(False)
+    ops.set_wgrad_strided_tc(False)
 dev = torch.device("cuda")
 layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=stride, padding=1).to(dev)
 x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)

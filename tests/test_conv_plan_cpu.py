@@ -280,7 +280,7 @@ def test_deinterleaved_halo_with_an_unstrided_depth_axis():
 def test_dispatch_table_of_the_luna_train_step():
     """scripts/dispatch_report.py: every convolution launch of the LUNA-shaped train step through the library's dry-run dispatch
     queries (host-only predicates, the ones the real dispatch uses).  Pins which layers ride on tcgen05 -- 88 % of the step's
-    8.24 TFLOP by default, 95 % with the opt-in strided kernels -- and that the opt-in kernels are picked for exactly the strided forms."""
+    8.24 TFLOP with the strided / transposed forms on mma.sync (round-1 default, experimental=False), 95 % with their tcgen05 kernels (default since round 2) -- picked for exactly the strided forms."""
     import importlib.util, os
     spec = importlib.util.spec_from_file_location("dispatch_report", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                                                  "scripts", "dispatch_report.py"))
@@ -296,9 +296,9 @@ def test_dispatch_table_of_the_luna_train_step():
     by = {r[0]: r for r in rows}
     assert 0.94 < frac_x < 0.96
     for l in (1, 2, 3, 4):
-        assert by[f"encoder.stage{l}.conv1"][5] == "conv_tc S2 (opt-in)" and by[f"encoder.stage{l}.conv1"][7] == "conv_wgrad_tc SW=2 (opt-in)"
+        assert by[f"encoder.stage{l}.conv1"][5] == "conv_tc S2" and by[f"encoder.stage{l}.conv1"][7] == "conv_wgrad_tc SW=2"
     for l in (1, 2, 3, 4):
-        assert by[f"decoder.up.P{l}"][6] == "conv_tc S2 (opt-in)" and by[f"decoder.up.P{l}"][7] == "conv_wgrad_tc SW=2 (opt-in)"
+        assert by[f"decoder.up.P{l}"][6] == "conv_tc S2" and by[f"decoder.up.P{l}"][7] == "conv_wgrad_tc SW=2"
     assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")         # stride-1 layers untouched
     _, _, frac_after = dr.report("luna", experimental=False, quiet=True)
     assert frac_after == frac                                                                      # switches restored

@@ -89,3 +89,32 @@ def test_state_round_trip(tmp_path):
     out = ens2.get_case_result()
     for k in ("pred_boxes", "pred_scores", "pred_labels"):
         assert torch.equal(out[k], ref[k])
+
+
+def test_restore_prediction_matches_the_executed_reference():
+    """`get_case_result(restore=True)` (the reference's production path: scripts/predict.py:99 -> predict_dir(restore=True)): boxes from the
+    preprocessed into the original image space, bit-exact against the executed `restore_detection` (nndet/inference/restore.py:30-66)
+    on four axis orders / spacings / crops (tests/golden/restore.npz, scripts/gen_golden.py restore)."""
+    from nndetection_b200.inference.ensembler import BoxEnsemblerSelective
+    g = util.golden("restore")
+    for i in range(int(g["n_cases"])):
+        props = dict(transpose_backward=g[f"tb{i}"].tolist(), original_spacing=g[f"osp{i}"], spacing_after_resampling=g[f"rsp{i}"],
+                     crop_bbox=[tuple(r) for r in g[f"crop{i}"].tolist()], itk_spacing=(1, 1, 1))
+        ens = BoxEnsemblerSelective.from_case({"data": torch.zeros(1, 8, 8, 8)}, properties=props)
+        out = ens.restore_prediction(torch.from_numpy(g[f"boxes{i}"]))
+        assert out.dtype == torch.float32 and torch.equal(out, torch.from_numpy(g[f"restored{i}"])), i
+    # through get_case_result: restored boxes + the flag, nothing raises
+    models, shape = util.synth_tile_predictions(1)
+    params = BoxEnsemblerSelective.get_default_parameters()
+    params.update({"model_nms_fn": _o_weighted_nms_model, "ensemble_nms_fn": _o_wbc_ensemble})
+    props = dict(transpose_backward=[2, 0, 1], original_spacing=(2.5, 0.7, 0.7), spacing_after_resampling=(0.8, 1.25, 0.9),
+                 crop_bbox=[(3, 90), (11, 200), (7, 150)], itk_spacing=(1, 1, 1))
+    ens = BoxEnsemblerSelective.from_case({"data": torch.zeros(1, *shape)}, properties=props, parameters=params)
+    for mi, batches in enumerate(models):
+        ens.add_model(name=f"m{mi}", model_weight=1.0)
+        for res, batch in batches:
+            ens.process_batch(result=res, batch=batch)
+    plain, restored = ens.get_case_result(restore=False), ens.get_case_result(restore=True)
+    assert restored["restore"] is True and plain["restore"] is False
+    assert torch.equal(restored["pred_boxes"], ens.restore_prediction(plain["pred_boxes"]))
+    assert torch.equal(restored["pred_scores"], plain["pred_scores"])

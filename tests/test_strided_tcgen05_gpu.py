@@ -1,9 +1,12 @@
-"""Kernels written WITHOUT a GPU at the end of round 1 (budget spent), switched off in the product until validated.  These tests
-switch them on; because an addressing bug in a tcgen05 kernel can poison the CUDA context for everything that follows, they only
-run when NND_EXPERIMENTAL=1 (scripts/gpu_checkup.sh runs them in their own process after the regular suite).
+"""The tcgen05 kernels for the strided / transposed forms (written without a GPU at the end of round 1, validated on a B200 in round 2
+and ON by default since): every test runs the layer with the switch on and off (mma.sync kernels) and checks both against the CPU oracle.
 
-  * nnd_conv_set_wgrad_strided_tc(1): weight gradient of stride-2 3x3x3 convolutions on tcgen05 (conv_wgrad_tc.cu, SW = 2: x rows
-    de-interleaved into an odd and an even plane so every tap is again 16 consecutive 16-byte rows)."""
+  * nnd_conv_set_wgrad_strided_tc: weight gradient of stride-2 3x3x3 convolutions and of kernel == stride transposed convolutions
+    (conv_wgrad_tc.cu, SW = 2: x rows de-interleaved into an odd and an even plane so every tap is again 16 consecutive 16-byte rows);
+  * nnd_conv_set_gather_strided_tc: stride-2 fprop and the up-convolutions' dgrad (conv_tc.cu, S2 = 1: per-axis de-interleaved halo);
+  * nnd_norm_set_bwd_narrow: four-channel norm backward passes (correct; no faster in the step: stays opt-in);
+  * nnd_conv_set_tc_bulk (cp.async.bulk weight stream in the tile kernel): DEADLOCKS on the device -- its test only runs with
+    NND_EXPERIMENTAL=1 in a process of its own, under a timeout."""
 import os
 from ctypes import c_int
 
@@ -13,8 +16,8 @@ import torch
 import tutil as util  # noqa: F401
 from test_net_gpu import make_pair, q, rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NND_EXPERIMENTAL") != "1", reason="unvalidated kernels: set NND_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
+_bulk_gate = pytest.mark.skipif(os.environ.get("NND_EXPERIMENTAL") != "1", reason="the bulk-copy variant deadlocks on the device: NND_EXPERIMENTAL=1 + a timeout")
 
 
 @pytest.mark.parametrize("cin,cout,s,shape", [
@@ -50,7 +53,7 @@ def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
                 kernels[mode] = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
-        ops.set_wgrad_strided_tc(False)
+        ops.set_wgrad_strided_tc(True)
     assert kernels[1] == ["wgrad_tc_s2"] and kernels[0] != ["wgrad_tc_s2"]
     assert rel_err(res[1], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[1], res[0]) < 1e-3
@@ -83,7 +86,7 @@ def test_transposed_conv_wgrad_on_tcgen05(cin, cout, s, shape):
                 kernels[mode] = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
-        ops.set_wgrad_strided_tc(False)
+        ops.set_wgrad_strided_tc(True)
     assert kernels[True] == ["wgrad_tc_s2"] and len(kernels[False]) == (8 if s == 2 else 4)
     assert rel_err(res[True], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[True], res[False]) < 1e-3
@@ -119,7 +122,7 @@ def test_strided_conv_block_forward_on_tcgen05(cin, cout, shape, s):
                 y, rows = _trace_kernels(ops, lambda: mine(xm))
             res[mode] = (y.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop"])
     finally:
-        ops.set_gather_strided_tc(False)
+        ops.set_gather_strided_tc(True)
     assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
     assert rel_err(res[True][0], yr) < 5e-3
     assert rel_err(res[True][0], res[False][0]) < 3e-3
@@ -144,7 +147,7 @@ def test_upconv_input_gradient_on_tcgen05(cin, cout, shape):
             _, rows = _trace_kernels(ops, lambda: mine(xm).backward(gy.cuda().to(torch.bfloat16)))
             res[mode] = (xm.grad.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop" and int(r["T"]) == 8])
     finally:
-        ops.set_gather_strided_tc(False)
+        ops.set_gather_strided_tc(True)
     assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
     assert rel_err(res[True][0], xr.grad) < 5e-3
     assert rel_err(res[True][0], res[False][0]) < 3e-3
@@ -162,6 +165,7 @@ def test_item_order_repack_kernel():
         assert ip.T == T and torch.equal(ip.data.view(-1), want.view(-1))
 
 
+@_bulk_gate
 @pytest.mark.parametrize("kind,cin,cout,k,shape", [
     ("instance", 128, 128, 3, (4, 32, 32, 32)),       # 4-slice tiles (>= one tile per SM)
     ("group", 128, 128, 3, (2, 8, 16, 16)),           # 2-slice tiles

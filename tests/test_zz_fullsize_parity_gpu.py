@@ -39,10 +39,19 @@ def test_one_full_size_patch_against_the_oracle(name, seed, max_gt):
     tg = {"target_boxes": [b.cuda() for b in targets["target_boxes"]], "target_classes": [c.cuda() for c in targets["target_classes"]],
           "target_seg": targets["target_seg"].cuda()}
     # --- device
+    # outputs of the SAME forward pass the losses were computed from (a second pass differs in the last bits: the norm statistics are
+    # accumulated with fp32 atomics)
+    seen = {}
+    h1 = net.head.register_forward_hook(lambda m, i, o: seen.__setitem__("det", {k: v.detach().clone() for k, v in o.items()}))
+    h2 = net.segmenter.register_forward_hook(lambda m, i, o: seen.__setitem__("seg", {k: v.detach().clone() for k, v in o.items()}))
     with torch.no_grad():
         losses, _ = net.train_step(images.cuda(), tg, evaluation=False, batch_num=0)
         pos_idx, neg_idx, counts, labels, matches = net.last_sample
-        pdet, anchors_d, pseg = net(images.cuda())
+    h1.remove(); h2.remove()
+    pdet, pseg = seen["det"], seen["seg"]
+    anchors_d = net.anchor_generator.lookup(images.cuda())
+    assert anchors_d is not None
+    anchors_d = [anchors_d[0]]
     cnt = counts.cpu().tolist()
     pos, neg = pos_idx[:cnt[2]].cpu(), neg_idx[:cnt[3]].cpu()
     # --- oracle

@@ -36,3 +36,30 @@ def test_sgd_step_matches_torch_optim_sgd(nesterov, world):
                                  L.stream_ptr()), "nnd_sgd_step")
         ref = torch.cat([pd.detach(), pn.detach()])
         assert torch.allclose(flat, ref, rtol=2e-6, atol=5e-7), (step, float((flat - ref).abs().max()))
+
+
+def test_parameters_without_a_gradient_are_left_alone_like_torch_sgd_does():
+    """torch.optim.SGD skips parameters whose `.grad is None` (no weight decay, no momentum).  In the reference that is e.g. decoder
+    `out.P1` of the LUNA plan (its output feeds neither head nor segmenter).  The flat-buffer optimizer finds those layers after the first
+    backward pass (layers whose backward never ran) and skips their element ranges (nnd_sgd_step_skip)."""
+    from nndetection_b200.configs import make_plan, synth_batch
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    from nndetection_b200.training import Trainer
+    arch, anc, patch, bs = make_plan("tiny")
+    arch = dict(arch, decoder_levels=(2,))                       # P0 -> segmenter, P1 -> nothing, P2 -> detection head
+    anc = {k: v[:1] for k, v in anc.items()}
+    torch.manual_seed(1)
+    net = RetinaUNetV001.from_config_plan(None, arch, anc).cuda()
+    before = {k: v.detach().clone() for k, v in net.named_parameters()}
+    trainer = Trainer(net, initial_lr=0.05, warm_iterations=1, warm_lr=0.05, num_iterations=10, weight_decay=1e-2)
+    for step in range(2):
+        images, targets = synth_batch(patch, bs, 1, arch["classifier_classes"], 50 + step)
+        tg = {"target_boxes": [b.cuda() for b in targets["target_boxes"]], "target_classes": [c.cuda() for c in targets["target_classes"]],
+              "target_seg": targets["target_seg"].cuda()}
+        trainer.train_step(images.cuda(), tg, evaluation=False)
+    assert sorted(trainer.fp.unused) == ["decoder.out.P1.0.conv.bias", "decoder.out.P1.0.conv.weight"]
+    after = dict(net.named_parameters())
+    for k in trainer.fp.unused:
+        assert torch.equal(after[k].detach(), before[k]), k      # bit-identical: neither decayed nor moved
+    changed = [k for k in before if k not in trainer.fp.unused and not torch.equal(after[k].detach(), before[k])]
+    assert len(changed) == len(before) - 2                        # every other parameter was updated
