@@ -115,6 +115,10 @@ class BaseRetinaNet(nn.Module):
                 labels = E.assign_labels(matches, gt, early[0].shape[0])
             pred_detection, anchors, pred_seg = self(images)
             cur.wait_stream(side)
+            # allocated under the side stream, consumed on the current one: tell the caching allocator, so that a block freed after
+            # this step cannot be handed out again on the side stream while the current stream still reads it
+            for t in (matches, labels, gt.boxes, gt.classes, gt.offsets, gt.img, gt.local):
+                t.record_stream(cur)
             a0 = anchors[0]
             A = a0.shape[0]
         else:
