@@ -283,11 +283,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
-    if args.trace_layers and rank == 0:
+    # ---- whole-step roofline: ONE extra step (outside the timed regions) with the per-launch convolution trace on
+    roof_step = None
+    if rank == 0 and world == 1:
+        import tempfile
+        trace_path = args.trace_layers or os.path.join(tempfile.mkdtemp(prefix="nnd_trace_"), "layers.csv")
         conv_ops.trace_start()
         step_resident(0)
-        rows = conv_ops.trace_dump(args.trace_layers)
-        print(f"[bench] wrote {rows} convolution launches of one train step to {args.trace_layers}", file=sys.stderr)
+        rows = conv_ops.trace_dump(trace_path)
+        roof_step = step_roofline(trace_path, ms / args.steps)
+        if args.trace_layers:
+            print(f"[bench] wrote {rows} convolution launches of one train step to {args.trace_layers}", file=sys.stderr)
 
     # ---- roofline of the dominant kernel family (gather convolution), measured live with CUDA events
     roof = None
@@ -306,7 +312,7 @@ def main():
                           "l2": f"{n_batches} distinct input batches; per-step activations (> 4 GB) exceed the 126 MB L2"},
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+               "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_step": roof_step,
                "train_tflops": 3 * conv_flops_per_patch(arch, patch) * bs * world * args.steps / (ms / 1e3) / 1e12}
         try:
             out["nms"] = nms_rates(dev)
@@ -418,6 +424,41 @@ def ref_nms_rates(dev):
 
 
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)
+
+
+def step_roofline(trace_csv, ms_step):
+    """The WHOLE step against the tensor roof (the single-kernel `roofline` block describes the best kernel,
+    not the step).  From the per-launch convolution trace of one extra step (nnd_conv_trace: two CUDA events around every
+    convolution-family launch, on its stream): per kernel family the summed launch time, the algorithmic FLOPs (2 * taps * Cin * Cout
+    per logical output voxel -- the transposed / parity forms counted once) and TFLOP/s as a fraction of the SUSTAINED measured bf16
+    peak (the launches run inside a long step); `other_ms` = step time - convolution launches = norm passes, box engine, losses, NMS,
+    optimizer, eager residual adds; `step` = all conv FLOPs / step time.  `tcgen05_flop_share` / `mma_sync_time_share` answer "how much
+    of the step still rides on mma.sync"."""
+    import csv, collections
+    _, _, tf_sus, kind = peaks()
+    fam = collections.defaultdict(lambda: [0.0, 0.0, 0])
+    for r in csv.DictReader(open(trace_csv)):
+        ms = float(r["ms"])
+        if ms < 0:
+            continue
+        f = fam[(r["kind"] if r["kind"] in ("wgrad", "first_fprop", "first_wgrad") else "fprop/dgrad", r["kernel"])]
+        f[0] += ms; f[1] += float(r["gflop"]); f[2] += 1
+    conv_ms = sum(v[0] for v in fam.values()); gf = sum(v[1] for v in fam.values())
+    mma_sync = {"conv_igemm", "wgrad_generic", "wgrad_halo", "conv_first"}
+    rows = [{"kind": k[0], "kernel": k[1], "launches": v[2], "ms": round(v[0], 4), "gflop": round(v[1], 1),
+             "tflops": round(v[1] / max(v[0], 1e-9), 1), "frac_of_sustained_peak": round(v[1] / max(v[0], 1e-9) / tf_sus, 4),
+             "share_of_step": round(v[0] / ms_step, 4), "path": "mma.sync" if k[1] in mma_sync else "tcgen05"}
+            for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])]
+    tc_gf = sum(v[1] for k, v in fam.items() if k[1] not in mma_sync)
+    return {"peak": tf_sus, "peak_kind": kind + " sustained bf16 cuBLAS", "unit": "TFLOP/s", "ms_step": ms_step, "conv_ms": round(conv_ms, 3),
+            "other_ms": round(ms_step - conv_ms, 3), "conv_gflop": round(gf, 1),
+            "step": {"tflops": round(gf / ms_step, 1), "frac": round(gf / ms_step / tf_sus, 4)},
+            "conv_only": {"tflops": round(gf / max(conv_ms, 1e-9), 1), "frac": round(gf / max(conv_ms, 1e-9) / tf_sus, 4)},
+            "tcgen05_flop_share": round(tc_gf / max(gf, 1e-9), 4),
+            "mma_sync_time_share": round(sum(v[0] for k, v in fam.items() if k[1] in mma_sync) / ms_step, 4),
+            "families": rows,
+            "note": "launch times from CUDA events inside one traced step (launches on forked streams may overlap: shares can sum past the "
+                    "step on those)"}
 
 
 def nms_rates(dev):

@@ -121,11 +121,11 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
  *      (csrc/conv_common.cuh): N,Di,Hi,Wi,Cin, Ld,Lh,Lw, sd,sh,sw, Do,Ho,Wo, omd,omh,omw, ood,ooh,oow, T, then per tap
  *      (off_d, off_h, off_w, weight_tap).  w: bf16 [T][CoutPad][Cin] from nnd_pack_weights.  Epilogue: +bias, +residual,
  *      *scale, optional fp32 output with sample / voxel strides (writes the [N, anchors, C] head layout directly),
- *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel, 3 tcgen05 stride-2 tile kernel (opt-in), 4 tcgen05 tile kernel with bulk-copied weights (opt-in). */
+ *      per-(sample, channel) sum / sum-of-squares for the following norm.  used_tc_host: 0 mma.sync kernel, 1 tcgen05 tile kernel, 2 tcgen05 streaming kernel, 3 tcgen05 stride-2 tile kernel, 4 tcgen05 tile kernel with bulk-copied weights (do not use), 5 TMA-fed pointwise tcgen05 GEMM. */
 void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
-void nnd_conv_set_wgrad_strided_tc(int enable);       /* opt-in (default 0): de-interleaved tcgen05 wgrad for stride-2 convolutions, not yet validated on a device */
-void nnd_conv_set_gather_strided_tc(int enable);      /* opt-in (default 0): de-interleaved-halo tcgen05 kernel for stride-2 gathers, not yet validated on a device */
+void nnd_conv_set_wgrad_strided_tc(int enable);       /* default 1 (validated on B200, round 2): de-interleaved tcgen05 wgrad for stride-2 / transposed convolutions; 0 = mma.sync (A/B) */
+void nnd_conv_set_gather_strided_tc(int enable);      /* default 1 (validated on B200, round 2): de-interleaved-halo tcgen05 kernel for stride-2 gathers; 0 = mma.sync (A/B) */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
 /* Profiling aid (off by default): one row per convolution-family launch -- kind (fprop | wgrad | first_*), the kernel the dispatch
  * chose, the geometry, and the launch's duration from two CUDA events on its stream.  trace(1) clears + starts, trace(0) stops;
@@ -134,15 +134,15 @@ void nnd_conv_trace(int enable);
 long long nnd_conv_trace_count(void);
 int nnd_conv_trace_dump(const char* path);
 /* Dry-run dispatch queries (host only, no CUDA call): the kernel that would serve a launch under the current switches.
- * gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2 (opt-in); wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
- * 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2 (opt-in); negative: bad geometry. */
+ * gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2, 4 conv_pw (TMA); wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
+ * 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2; negative: bad geometry. */
 int nnd_conv_gather_dispatch(const int* geom_host, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
                              int has_bias, int has_residual, int has_stats);
 int nnd_conv_wgrad_dispatch(const int* geom_host, int Cdy, int Cx);
 int nnd_conv_gather_bf16(const void* in, const void* w, const int* geom_host, void* out, long long out_n_stride,
                          long long out_v_stride, int out_fp32, int Cout, int CoutPad, const float* bias, const float* scale,
                          const void* residual, float* stat_sum, float* stat_sq, int* used_tc_host, cudaStream_t stream);
-/* Opt-in (default off, not yet validated on a device): the tile kernel's weight stream through cp.async.bulk.  The caller re-packs a
+/* DO NOT ENABLE (deadlocks on the device; kept as the record of the experiment): the tile kernel's weight stream through cp.async.bulk.  The caller re-packs a
  * K-major weight pack [T][rows_pad][K] into pipeline-item order [row tile][k chunk][T][k group][n][8] (kg = 4: 32-channel chunks)
  * and passes it along with the ordinary pack; used only while nnd_conv_set_tc_bulk(1). */
 void nnd_conv_set_tc_bulk(int enable);
@@ -183,6 +183,15 @@ int nnd_seg_loss_bwd(const float* logits, const float* target, const double* sum
                      const float* up_ce, const float* up_dice, float* dlogits, cudaStream_t stream);
 int nnd_seg_conv_bwd(const void* x, int C, const float* w, const float* dlogits, long long total, void* dx, float* dw, float* db,
                      cudaStream_t stream);
+
+/* ---- TMA-fed pointwise GEMM (csrc/conv_pw.cu).  nnd_conv_set_pointwise_tma(1): single-tap launches of nnd_conv_gather_bf16 (1x1x1
+ *      convolutions = U-FPN laterals, nndet/arch/decoder/base.py:216-241, their dgrad, parity classes of up-convolutions) take it.
+ *      nnd_conv_upconv_bf16: a whole kernel == stride nn.ConvTranspose3d (decoder/base.py:272-304) in one launch; x bf16 [N,D,H,W,Cin],
+ *      w_packed = fprop pack of nnd_pack_weights ([taps][Cout][Cin], taps (a,b,c) row-major), out / residual bf16
+ *      [N, D*sd, H*sh, W*sw, Cout]; Cin, Cout multiples of 32, strides in {1, 2}. */
+void nnd_conv_set_pointwise_tma(int enable);
+int nnd_conv_upconv_bf16(const void* x, const void* w_packed, int N, int D, int H, int W, int Cin, int Cout, int sd, int sh, int sw,
+                         void* out, const float* bias, const void* residual, cudaStream_t stream);
 
 /* ---- optimizer + small streaming helpers.  nnd_sgd_step == torch.optim.SGD(momentum, nesterov, weight_decay) as configured in
  *      nndet/ptmodule/retinaunet/base.py:300-336; elements >= n_decay get no weight decay (norm params). */

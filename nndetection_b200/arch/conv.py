@@ -124,6 +124,10 @@ class _ConvBlockFn(torch.autograd.Function):
         if first:
             ops.conv_first_fprop(x, weight.detach(), plan.fprop[0], cout, y, stats[0] if has_norm else None,
                                  stats[1] if has_norm else None)
+        elif (conv.transposed and not has_norm and ops.pointwise_tma_enabled() and N * x.shape[2] * x.shape[3] * x.shape[4] >= 128
+              and all(v in (1, 2) for v in plan.s)):
+            # the whole up-convolution in one launch: taps stacked along N, the lateral added in the epilogue
+            ops.conv_upconv(x, wp_f, N, tuple(x.shape[2:]), cin, cout, plan.s, y, bias.detach() if bias is not None else None, res)
         else:
             items_f = layer.packed_items()[0]
             for g in plan.fprop:

@@ -247,6 +247,28 @@ def set_gather_strided_tc(enable: bool):
     L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
 
 
+_PW_TMA = False
+
+
+def set_pointwise_tma(enable: bool):
+    """TMA-fed tcgen05 GEMM (csrc/conv_pw.cu) for single-tap gathers -- 1x1x1 convolutions and their input gradients, parity classes of
+    up-convolutions -- and, through `conv_upconv`, whole kernel == stride transposed convolutions in one launch."""
+    global _PW_TMA
+    L.lib().nnd_conv_set_pointwise_tma(c_int(1 if enable else 0))
+    _PW_TMA = bool(enable)
+
+
+def pointwise_tma_enabled() -> bool:
+    return _PW_TMA
+
+
+def conv_upconv(x: Tensor, w_packed: Tensor, N: int, in_sp, cin: int, cout: int, s, out: Tensor, bias=None, residual=None):
+    """nn.ConvTranspose3d with kernel == stride in one launch (taps stacked along N, each input voxel read once, lateral added)."""
+    L.check(L.lib().nnd_conv_upconv_bf16(L.ptr(x), L.ptr(w_packed), c_int(N), c_int(in_sp[0]), c_int(in_sp[1]), c_int(in_sp[2]), c_int(cin),
+                                         c_int(cout), c_int(s[0]), c_int(s[1]), c_int(s[2]), L.ptr(out), L.ptr(bias), L.ptr(residual),
+                                         L.stream_ptr()), "nnd_conv_upconv_bf16")
+
+
 def wgrad_strided_tc_enabled() -> bool:
     return _WGRAD_STRIDED_TC
 

@@ -16,6 +16,10 @@ int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tc_bulk_supported(const ConvGeom& g, const ConvEpilogue& ep, const void* items, int items_n_tile, int items_T);
 int nnd_conv_tc_bulk(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st,
                      const __nv_bfloat16* items, int items_n_tile, int items_T);
+int nnd_conv_pw(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_pw_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_upconv(const void* x, const void* w_packed, int N, int D, int H, int W, int Cin, int Cout, int sd, int sh, int sw,
+                    void* out, const float* bias, const void* residual, cudaStream_t st);
 int nnd_conv_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tcs_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tcs_profitable(const ConvGeom& g, const ConvEpilogue& ep);
@@ -62,6 +66,7 @@ int g_stream = 1;
 int g_wgrad_strided = 1;      // validated on a B200 in round 2 (tests/test_strided_tcgen05_gpu.py), default since
 int g_gather_strided = 1;
 int g_tc_bulk = 0;
+int g_pw = 0;                 // TMA-fed pointwise GEMM (conv_pw.cu) for single-tap gathers
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
 // ncu names kernels, not layers; this table is what maps the step time onto the network.
@@ -111,6 +116,9 @@ void nnd_conv_set_gather_strided_tc(int enable) { g_gather_strided = enable; }
 // 1: launches that bring an item-order weight pack (nnd_conv_gather_bf16_items) stream it with cp.async.bulk (conv_tc.cu, BULK = 1).
 // Default 0: the variant DEADLOCKS on the device (round-2 run: its test hit the 200 s timeout) -- kept only as a record, do not enable.
 void nnd_conv_set_tc_bulk(int enable) { g_tc_bulk = enable; }
+// 1: single-tap gathers (1x1x1 convolutions and their dgrad, parity classes of up-convolutions) take the TMA-fed tcgen05 GEMM of
+// conv_pw.cu instead of the mma.sync gather kernel.
+void nnd_conv_set_pointwise_tma(int enable) { g_pw = enable; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -161,6 +169,7 @@ int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long 
   ep.residual = has_residual ? reinterpret_cast<const __nv_bfloat16*>(&dummy) : nullptr;
   ep.stat_sum = has_stats ? &dummy : nullptr; ep.stat_sq = has_stats ? &dummy : nullptr;
   if (g_force_igemm) return 0;
+  if (g_pw && nnd_conv_pw_supported(g, ep)) return 4;
   if (g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) return 2;
   if (g_gather_strided && nnd_conv_tc_s2_supported(g, ep)) return 3;
   return nnd_conv_tc_supported(g, ep) ? 1 : 0;
@@ -201,6 +210,11 @@ int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, v
   ep.out = out; ep.out_n_stride = out_n_stride; ep.out_v_stride = out_v_stride; ep.out_fp32 = out_fp32;
   ep.Cout = Cout; ep.CoutPad = CoutPad; ep.bias = bias; ep.scale = scale;
   ep.residual = (const __nv_bfloat16*)residual; ep.stat_sum = stat_sum; ep.stat_sq = stat_sq;
+  if (!g_force_igemm && g_pw && nnd_conv_pw_supported(g, ep)) {
+    if (used_tc) *used_tc = 5;
+    TraceScope ts("fprop", "conv_pw", g, g.Cin, Cout, st);
+    return nnd_conv_pw((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+  }
   if (!g_force_igemm && g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) {
     if (used_tc) *used_tc = 2;
     TraceScope ts("fprop", "conv_tcs", g, g.Cin, Cout, st);
@@ -221,6 +235,16 @@ int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, v
   TraceScope ts("fprop", tc ? "conv_tc" : "conv_igemm", g, g.Cin, Cout, st);
   if (tc) return nnd_conv_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
   return nnd_conv_igemm((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+}
+
+// conv_pw.cu: a whole kernel == stride transposed convolution in one launch (see include/nndet_b200.h)
+int nnd_conv_upconv_bf16(const void* x, const void* w_packed, int N, int D, int H, int W, int Cin, int Cout, int sd, int sh, int sw,
+                         void* out, const float* bias, const void* residual, cudaStream_t st) {
+  ConvGeom g = {};
+  g.N = N; g.Di = D; g.Hi = H; g.Wi = W; g.Cin = Cin; g.Ld = D; g.Lh = H; g.Lw = W; g.sd = sd; g.sh = sh; g.sw = sw;
+  g.T = sd * sh * sw;                                   // trace row: taps x input voxels (the dump's FLOP formula)
+  TraceScope ts("fprop", "conv_pw_up", g, Cin, Cout, st);
+  return nnd_conv_upconv(x, w_packed, N, D, H, W, Cin, Cout, sd, sh, sw, out, bias, residual, st);
 }
 
 int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom, float* dw, long long s_co,
