@@ -176,27 +176,35 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
       }
       const unsigned a_base = smem_u32(sA + astage * A_BYTES);
       const __nv_bfloat16* in_n = in + (size_t)n * g.Di * g.Hi * g.Wi * g.Cin + kc * (8 * KG);
-      // Lane mapping: consecutive lanes copy the KG consecutive 16-byte channel groups of ONE voxel (whole 32-byte sectors per warp
-      // instruction), then the next voxel of the row.  The round-1 mapping (one thread per (group, z, y) row walking x) fetched every
-      // sector twice from two different instructions: 2x the operand bytes on the L2 -> SM path.
-      constexpr int HCHUNKS = HROWS * HX;              // 16-byte chunks of one halo
-      for (int c = tid; c < HCHUNKS; c += NUM_PROD) {
-        const int gidx = c % KG; int t = c / KG;
-        const int xv = t % HX; t /= HX;
-        const int y = t % HY, z = t / HY;
-        const unsigned dst_row = a_base + (((gidx * HALO_SLICES + z) * HY + y) * HX) * 16;
+      for (int rr = tid; rr < HROWS; rr += NUM_PROD) {
+        const int gidx = rr / (HALO_SLICES * HY); const int r2 = rr - gidx * (HALO_SLICES * HY);
+        const int z = r2 / HY, y = r2 - z * HY;
         if (!S2) {
-          const int d = d0 - 1 + z, h = h0 - 1 + y, w = w0 - 1 + xv;
-          const bool ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi && (unsigned)w < (unsigned)g.Wi;
-          cp_async16(dst_row + xv * 16, ok ? in_n + ((long long)(d * g.Hi + h) * g.Wi + w) * g.Cin + gidx * 8 : in, ok);
+        const int d = d0 - 1 + z, h = h0 - 1 + y;
+        const bool row_ok = (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
+        const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + (w0 - 1)) * g.Cin + gidx * 8;
+        unsigned dst = a_base + rr * (HX * 16);
+#pragma unroll
+        for (int x = 0; x < HX; ++x) {
+          const bool ok = row_ok && (unsigned)(w0 - 1 + x) < (unsigned)g.Wi;
+          cp_async16(dst, ok ? src : in, ok);
+          dst += 16; src += g.Cin;
+        }
         } else {
           // slot -> input position: odd plane slot p -> 2 (o0 + p) - 1, even plane slot n + 1 + p -> 2 (o0 + p)
           const int d = g.sd == 2 ? (z <= MT ? 2 * (d0 + z) - 1 : 2 * (d0 + z - (MT + 1))) : d0 - 1 + z;
           const int h = y <= BH ? 2 * (h0 + y) - 1 : 2 * (h0 + y - (BH + 1));
-          const int w = 2 * w0 - 1 + xv;                 // xv-th input voxel of the row: even xv -> odd plane, odd xv -> even plane
-          const bool ok = (g.sd == 2 || z < MT + 2) && (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi && (unsigned)w < (unsigned)g.Wi;
-          const int slot = (xv & 1) ? (BW + 1) + (xv >> 1) : (xv >> 1);
-          cp_async16(dst_row + slot * 16, ok ? in_n + ((long long)(d * g.Hi + h) * g.Wi + w) * g.Cin + gidx * 8 : in, ok);
+          const bool row_ok = (g.sd == 2 || z < MT + 2) && (unsigned)d < (unsigned)g.Di && (unsigned)h < (unsigned)g.Hi;
+          const int w_in0 = 2 * w0 - 1;
+          const __nv_bfloat16* src = in_n + ((long long)(d * g.Hi + h) * g.Wi + w_in0) * g.Cin + gidx * 8;
+          const unsigned dst0 = a_base + rr * (HX * 16);
+#pragma unroll
+          for (int v = 0; v < HX; ++v) {                 // v-th input voxel of the row: even v -> odd plane, odd v -> even plane
+            const bool ok = row_ok && (unsigned)(w_in0 + v) < (unsigned)g.Wi;
+            const int slot = (v & 1) ? (BW + 1) + (v >> 1) : (v >> 1);
+            cp_async16(dst0 + slot * 16, ok ? src : in, ok);
+            src += g.Cin;
+          }
         }
       }
       if (BULK) {                                   // publish the halo on its own barrier as soon as it has landed
@@ -237,12 +245,11 @@ conv_tc_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __rest
         if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
         {
           const unsigned b_base = smem_u32(sB + slot * B_BYTES);
-          // lanes = the KG consecutive 16-byte k-groups of one weight row (whole sectors per instruction), then the next row
           for (int i = tid; i < TG * N_TILE * KG; i += NUM_PROD) {
-            const int kg = i % KG; const int r = i / KG;
-            const int nr = r % N_TILE, tt = r / N_TILE;
+            const int tt = i / (N_TILE * KG); const int r = i - tt * (N_TILE * KG);
+            const int kg = r / N_TILE, nr = r - kg * N_TILE;
             const __nv_bfloat16* wsrc = wbase + (size_t)g.tap_w[it * TG + tt] * ep.CoutPad * g.Cin;
-            cp_async16(b_base + ((tt * KG + kg) * N_TILE + nr) * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
+            cp_async16(b_base + i * 16, wsrc + (size_t)nr * g.Cin + kg * 8, true);
           }
         }
         cp_async_commit();

@@ -11,6 +11,9 @@
 // N_T-channel ci tile, one contiguous range of voxel rows (split-K).  4 producer warps (cp.async, zero fill = padding)
 // -> 4-stage ring -> 3 issuer warps (one per dx tap, independent accumulators) -> 4 epilogue warps (tcgen05.ld ->
 // fp32 atomicAdd into dW, PyTorch weight layout).
+// (Round-2 A/B: a producer mapping with consecutive lanes on consecutive channel groups of one voxel + a 16-byte padded group pitch
+// ran 2-4x SLOWER on the B200 -- 128->128 @32^3: 2.91 vs 1.35 ms -- and was reverted; the mapping below already covers 128 contiguous
+// bytes per row with lanes 0, 4, 8 ... of each instruction.)
 //
 // SW = 2 (opt-in until validated on the device, nnd_conv_set_wgrad_strided_tc): the same kernel for stride-2 convolutions,
 //   dW[tap][co][ci] = sum_o dy[o][co] * x[o * s + off_tap][ci].
@@ -51,10 +54,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc_kernel(const WtArgs a) {
   constexpr int XW = SW == 1 ? RW + 2 : 2 * RW + 1;      // x row slots: 18 (halo row) or 17 + 16 (odd / even plane)
   constexpr int A_GROUPS = M_T / 8, B_GROUPS = N_T / 8;
-  // +16: consecutive channel groups land 16 bytes apart modulo the 128-byte bank window, so that the producers' warp-wide copies
-  // (lanes = consecutive channel groups of one voxel, see below) spread over all banks instead of piling onto one
-  constexpr int A_GPITCH = ROWS * RW * 16 + 16;          // bytes between co groups inside a stage
-  constexpr int B_GPITCH = ROWS * XW * 16 + 16;          // bytes between ci groups
+  constexpr int A_GPITCH = ROWS * RW * 16;               // bytes between co groups inside a stage
+  constexpr int B_GPITCH = ROWS * XW * 16;               // bytes between ci groups
   constexpr int A_BYTES = A_GROUPS * A_GPITCH, B_BYTES = B_GROUPS * B_GPITCH;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 3 * N_T > 256 ? 512 : (3 * N_T > 128 ? 256 : 128);
@@ -105,52 +106,47 @@ conv_wgrad_tc_kernel(const WtArgs a) {
       __syncwarp();
       const unsigned sa = smem_u32(smem + stage * STAGE_BYTES), sb = sa + A_BYTES;
       // A: dy rows  [co group][row][16 voxels]   B: x rows [ci group][row][18 voxels]
-      // Lane mapping: consecutive lanes copy consecutive CHANNEL GROUPS (16 bytes each) of the same voxel, i.e. one warp instruction
-      // reads whole 32-byte sectors / 128-byte lines of the NDHWC tensor.  (One thread per (group, row) walking the voxels -- the
-      // round-1 mapping -- touched every sector twice from different instructions: ncu showed 2x the operand bytes crossing L2 -> SM.)
-      // The (n, d, h, wseg) coordinates of the stage's ROWS rows are decoded by lanes 0..ROWS-1 and broadcast.
-      int r_ws = 0, r_h = 0, r_d = 0, r_n = 0, r_ok = 0;
-      if (lane < ROWS) {
-        const long long row = r0 + (long long)s * ROWS + lane;
-        r_ok = row < r1;
-        if (r_ok) { r_ws = (int)(row % a.wsegs); long long q = row / a.wsegs; r_h = (int)(q % a.H); q /= a.H; r_d = (int)(q % a.D); r_n = (int)(q / a.D); }
-      }
-#pragma unroll 1
-      for (int rr = 0; rr < ROWS; ++rr) {
-        const bool row_ok0 = __shfl_sync(0xffffffffu, r_ok, rr) != 0;
-        const int ws = __shfl_sync(0xffffffffu, r_ws, rr), h = __shfl_sync(0xffffffffu, r_h, rr);
-        const int d = __shfl_sync(0xffffffffu, r_d, rr), n = __shfl_sync(0xffffffffu, r_n, rr);
-        {   // ---- A: co_groups x RW chunks of this row
-          const __nv_bfloat16* rowp = a.dy + ((((long long)n * a.D + d) * a.H + h) * a.W + ws * RW) * a.Cdy + co0;
-          const unsigned dst0 = sa + rr * (RW * 16);
+      const int a_items = co_groups * ROWS, b_items = B_GROUPS * ROWS;
+      for (int it = tid; it < a_items + b_items; it += NPROD) {
+        const bool isA = it < a_items;
+        const int j = isA ? it : it - a_items;
+        const int gidx = j / ROWS, rr = j % ROWS;
+        const long long row = r0 + (long long)s * ROWS + rr;
+        bool row_ok = row < r1;
+        int ws = 0, h = 0, d = 0, n = 0;
+        if (row_ok) { ws = (int)(row % a.wsegs); long long q = row / a.wsegs; h = (int)(q % a.H); q /= a.H; d = (int)(q % a.D); n = (int)(q / a.D); }
+        if (isA) {
+          const __nv_bfloat16* src = a.dy + ((((long long)n * a.D + d) * a.H + h) * a.W + ws * RW) * a.Cdy + co0 + gidx * 8;
+          unsigned dst = sa + gidx * A_GPITCH + rr * (RW * 16);
 #pragma unroll
-          for (int c = tid; c < A_GROUPS * RW; c += NPROD) {        // 16 lanes per voxel; lanes beyond the tile's real groups idle
-            const int gidx = c % A_GROUPS, v = c / A_GROUPS;
-            const bool ok = row_ok0 && ws * RW + v < a.W;
-            if (gidx < co_groups) cp_async16(dst0 + gidx * A_GPITCH + v * 16, ok ? rowp + (long long)v * a.Cdy + gidx * 8 : a.dy, ok);
+          for (int v = 0; v < RW; ++v) {
+            const bool ok = row_ok && ws * RW + v < a.W;
+            cp_async16(dst, ok ? src : a.dy, ok);
+            dst += 16; src += a.Cdy;
           }
-        }
-        if (SW == 1) {
+        } else if (SW == 1) {
           const int dd = d + dz, hh = h + dyo;
-          const bool row_ok = row_ok0 && (unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H;
-          const __nv_bfloat16* rowp = a.x + ((((long long)n * a.D + dd) * a.H + hh) * a.W + (ws * RW - 1)) * a.Cx + ci0;
-          const unsigned dst0 = sb + rr * (XW * 16);
-          for (int c = tid; c < B_GROUPS * XW; c += NPROD) {
-            const int gidx = c % B_GROUPS, v = c / B_GROUPS;
+          row_ok = row_ok && (unsigned)dd < (unsigned)a.D && (unsigned)hh < (unsigned)a.H;
+          const __nv_bfloat16* src = a.x + ((((long long)n * a.D + dd) * a.H + hh) * a.W + (ws * RW - 1)) * a.Cx + ci0 + gidx * 8;
+          unsigned dst = sb + gidx * B_GPITCH + rr * (XW * 16);
+#pragma unroll
+          for (int v = 0; v < XW; ++v) {
             const bool ok = row_ok && (unsigned)(ws * RW - 1 + v) < (unsigned)a.W;
-            cp_async16(dst0 + gidx * B_GPITCH + v * 16, ok ? rowp + (long long)v * a.Cx + gidx * 8 : a.x, ok);
+            cp_async16(dst, ok ? src : a.x, ok);
+            dst += 16; src += a.Cx;
           }
         } else {
           const int dd = d * a.sd + dz, hh = h * a.sh + dyo;
-          const bool row_ok = row_ok0 && (unsigned)dd < (unsigned)a.Di && (unsigned)hh < (unsigned)a.Hi;
+          row_ok = row_ok && (unsigned)dd < (unsigned)a.Di && (unsigned)hh < (unsigned)a.Hi;
           const int w_in0 = ws * RW * 2 - 1;                       // input voxel of slot v = 0 (odd plane, p = 0)
-          const __nv_bfloat16* rowp = a.x + ((((long long)n * a.Di + dd) * a.Hi + hh) * a.Wi + w_in0) * a.Cx + ci0;
-          const unsigned dst0 = sb + rr * (XW * 16);
-          for (int c = tid; c < B_GROUPS * XW; c += NPROD) {       // v-th input voxel of the row: even v -> odd plane, odd v -> even plane
-            const int gidx = c % B_GROUPS, v = c / B_GROUPS;
+          const __nv_bfloat16* src = a.x + ((((long long)n * a.Di + dd) * a.Hi + hh) * a.Wi + w_in0) * a.Cx + ci0 + gidx * 8;
+          const unsigned dst0 = sb + gidx * B_GPITCH + rr * (XW * 16);
+#pragma unroll
+          for (int v = 0; v < XW; ++v) {                           // v-th input voxel of the row: even v -> odd plane, odd v -> even plane
             const bool ok = row_ok && (unsigned)(w_in0 + v) < (unsigned)a.Wi;
             const int slot = (v & 1) ? (RW + 1) + (v >> 1) : (v >> 1);
-            cp_async16(dst0 + gidx * B_GPITCH + slot * 16, ok ? rowp + (long long)v * a.Cx + gidx * 8 : a.x, ok);
+            cp_async16(dst0 + slot * 16, ok ? src : a.x, ok);
+            src += a.Cx;
           }
         }
       }
@@ -249,7 +245,7 @@ int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
   a.rows_per_split = (a.total_rows + splits - 1) / splits;
   a.rows_per_split = (a.rows_per_split + ROWS - 1) / ROWS * ROWS;
   splits = (a.total_rows + a.rows_per_split - 1) / a.rows_per_split;
-  constexpr size_t SMEM = (size_t)STAGES * ((M_T / 8) * (ROWS * RW * 16 + 16) + (N_T / 8) * (ROWS * XW * 16 + 16)) + 8 * (2 * STAGES + 1);
+  constexpr size_t SMEM = (size_t)STAGES * ((M_T / 8) * ROWS * RW * 16 + (N_T / 8) * ROWS * XW * 16) + 8 * (2 * STAGES + 1);
   static NndPerDeviceOnce attr_set;
   if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<N_T, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));

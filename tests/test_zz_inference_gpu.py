@@ -112,4 +112,7 @@ def test_device_pipeline_with_the_network_matches_cpu_pipeline():
     b = out_d["pred_boxes"]
     if b.shape[0]:
         lim = torch.tensor([48, 96, 48, 96, 80, 80], device=b.device, dtype=b.dtype)
-        assert (b >= 0).all() and (b <= lim).all()
+        # consolidated boxes are score-weighted MEANS of clipped boxes (wbc.py:193-194): inside the case in exact arithmetic, but the
+        # fp32 quotient sum(w * b) / sum(w) of boxes that all touch a border may land an ulp outside (this assert without the slack is
+        # what failed in the round-1 driver run and again in the round-2 full-suite run: 96.00001 <= 96 -- the atomics' order decides)
+        assert (b >= -1e-3).all() and (b <= lim + 1e-3).all(), (b.min(0).values, b.max(0).values)
