@@ -196,6 +196,10 @@ def main():
     if "mma_s2" in args.experimental.split(","):             # A/B: strided / transposed forms back on the mma.sync kernels (round-1 default)
         conv_ops.set_wgrad_strided_tc(False)
         conv_ops.set_gather_strided_tc(False)
+    if "pw_tma" in args.experimental.split(","):             # TMA-fed pointwise GEMM for laterals / up-convolutions (conv_pw.cu)
+        conv_ops.set_pointwise_tma(True)
+    if "no_pw_tma" in args.experimental.split(","):
+        conv_ops.set_pointwise_tma(False)
     if "tc_bulk" in args.experimental.split(","):
         conv_ops.set_tc_bulk(True)
     if "norm_narrow" in args.experimental.split(","):

@@ -247,7 +247,7 @@ def set_gather_strided_tc(enable: bool):
     L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
 
 
-_PW_TMA = False
+_PW_TMA = True           # default since its validation on a B200 (round 2); the C side has the same default
 
 
 def set_pointwise_tma(enable: bool):

@@ -66,7 +66,7 @@ int g_stream = 1;
 int g_wgrad_strided = 1;      // validated on a B200 in round 2 (tests/test_strided_tcgen05_gpu.py), default since
 int g_gather_strided = 1;
 int g_tc_bulk = 0;
-int g_pw = 0;                 // TMA-fed pointwise GEMM (conv_pw.cu) for single-tap gathers
+int g_pw = 1;                 // TMA-fed pointwise GEMM (conv_pw.cu) for single-tap gathers (validated on a B200 in round 2; 0 = A/B)
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
 // ncu names kernels, not layers; this table is what maps the step time onto the network.

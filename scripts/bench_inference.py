@@ -57,7 +57,24 @@ def main():
         res = pred.ensembler.get_case_result()
         torch.cuda.synchronize()
         post = time.perf_counter() - t1
+        # the post-processing SWEEP of the reference (ensembler/detection.py:975-995 through sweeper.py:108-213): the whole-case NMS + WBC
+        # re-run for every candidate value of every swept parameter (6 + 2 + 6 + 7 + 7 = 28 settings) on the case's saved tile detections
+        _, sweep = BoxEnsemblerSelective.sweep_parameters()
+        base = dict(pred.ensembler.parameters)
+        t2 = time.perf_counter()
+        n_settings, n_boxes = 0, 0
+        for key, values in sweep.items():
+            for v in values:
+                pred.ensembler.update_parameters(**{key: v})
+                r = pred.ensembler.get_case_result()
+                n_settings += 1; n_boxes += int(r["pred_boxes"].shape[0])
+            pred.ensembler.update_parameters(**{key: base[key]})
+        torch.cuda.synchronize()
+        sweep_s = time.perf_counter() - t2
+        cand = sum(int(b.shape[0]) for m in pred.ensembler.model_results.values() for b in m["boxes"])
         print(json.dumps({"metric": "sliding-window inference, 160^3 patches", "value": n_tiles * len(pred.tta_dims) / dt, "unit": "patches/s",
+                          "sweep": {"settings": n_settings, "s_total": sweep_s, "s_per_setting": sweep_s / max(n_settings, 1),
+                                    "tile_detections_in": cand, "candidate_boxes_per_s": cand * n_settings / max(sweep_s, 1e-9)},
                           "n_gpus": world, "case": args.case, "tiles": n_tiles, "tta": len(pred.tta_dims), "batch": args.batch,
                           "s_per_case": dt, "s_whole_case_nms_wbc": post, "detections": int(res["pred_boxes"].shape[0]),
                           "data": "synthetic", "weights": "random init"}), flush=True)

@@ -13,7 +13,7 @@ from ctypes import c_int, c_longlong
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2"}
+GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2", 4: "conv_pw (TMA)"}
 WGRAD = {0: "wgrad generic (mma.sync)", 1: "wgrad halo (mma.sync)", 2: "conv_wgrad_tc", 3: "conv_wgrad_tc32", 4: "conv_wgrad_tcn",
          5: "conv_wgrad_tc SW=2"}
 
@@ -82,7 +82,11 @@ def report(config="luna", experimental=True, quiet=False):      # experimental=F
         vox_out = bs * int(np.prod(plan.out_sp))
         gf = 2.0 * cin * cout * T * (bs * int(np.prod(in_sp)) if tr else vox_out) * 1e-9
         fk = set()
-        for g in plan.fprop:
+        from nndetection_b200.arch import conv_ops
+        stacked = tr and not norm and conv_ops.pointwise_tma_enabled() and bs * int(np.prod(in_sp)) >= 128 and all(v in (1, 2) for v in plan.s)
+        if stacked:                                      # arch/conv.py: the whole up-convolution in one launch (nnd_conv_upconv_bf16)
+            fk.add("conv_pw (TMA)")
+        for g in ([] if stacked else plan.fprop):
             if head_out is not None:                    # fp32 outputs written straight into the [N, anchors, C] tensors
                 code = lib.nnd_conv_gather_dispatch(g, c_longlong(10 ** 9), c_longlong(head_out), c_int(1), c_int(head_out), c_int(cdy), c_int(1), c_int(0), c_int(0))
             else:

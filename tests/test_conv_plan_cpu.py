@@ -279,22 +279,26 @@ def test_deinterleaved_halo_with_an_unstrided_depth_axis():
 
 def test_dispatch_table_of_the_luna_train_step():
     """scripts/dispatch_report.py: every convolution launch of the LUNA-shaped train step through the library's dry-run dispatch
-    queries (host-only predicates, the ones the real dispatch uses).  Pins which layers ride on tcgen05 -- 88 % of the step's
-    8.24 TFLOP with the strided / transposed forms on mma.sync (round-1 default, experimental=False), 95 % with their tcgen05 kernels (default since round 2) -- picked for exactly the strided forms."""
+    queries (host-only predicates, the ones the real dispatch uses).  Pins which layers ride on tcgen05 -- 90 % of the step's
+    8.24 TFLOP with the strided / transposed forms on mma.sync (round-1 default, experimental=False), 97 % with their tcgen05 kernels and the TMA pointwise GEMM (defaults since round 2) -- picked for exactly the strided forms."""
     import importlib.util, os
     spec = importlib.util.spec_from_file_location("dispatch_report", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                                                  "scripts", "dispatch_report.py"))
     dr = importlib.util.module_from_spec(spec); spec.loader.exec_module(dr)
     rows, totals, frac = dr.report("luna", experimental=False, quiet=True)
     by = {r[0]: r for r in rows}
-    assert abs(sum(totals.values()) - 8242) < 15 and 0.87 < frac < 0.90
+    assert abs(sum(totals.values()) - 8242) < 15 and 0.89 < frac < 0.92
     assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")
     assert by["encoder.stage2.conv2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tc")
     assert by["encoder.stage1.conv1"][5] == "conv_igemm (mma.sync)" and by["encoder.stage1.conv1"][7] == "wgrad halo (mma.sync)"
     assert by["head.regressor.conv_out@P2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tc")
     rows, totals, frac_x = dr.report("luna", experimental=True, quiet=True)
     by = {r[0]: r for r in rows}
-    assert 0.94 < frac_x < 0.96
+    assert 0.96 < frac_x < 0.985
+    for l in (0, 1, 2, 3):
+        assert by[f"decoder.lateral.P{l}"][5] == "conv_pw (TMA)" and by[f"decoder.lateral.P{l}"][6] == "conv_pw (TMA)"        # 1x1x1: fprop + dgrad
+    for l in (1, 2, 3, 4):
+        assert by[f"decoder.up.P{l}"][5] == "conv_pw (TMA)"                                     # whole up-convolution in one launch
     for l in (1, 2, 3, 4):
         assert by[f"encoder.stage{l}.conv1"][5] == "conv_tc S2" and by[f"encoder.stage{l}.conv1"][7] == "conv_wgrad_tc SW=2"
     for l in (1, 2, 3, 4):

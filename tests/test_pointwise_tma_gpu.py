@@ -59,7 +59,7 @@ def test_pointwise_conv_forward_and_input_gradient(cin, cout, shape):
             ym, ks = _kernels(run)
             out[mode] = (ym.detach().float().cpu(), xm.grad.float().cpu(), mine.conv.weight.grad.cpu().clone(), ks)
     finally:
-        ops.set_pointwise_tma(False)
+        ops.set_pointwise_tma(True)
     ym, gx, gw, ks = out[True]
     assert [k for kind, k in ks if kind == "fprop"] == ["conv_pw", "conv_pw"]            # forward + input gradient
     assert "conv_pw" not in [k for _, k in out[False][3]]
@@ -95,7 +95,7 @@ def test_whole_upconvolution_in_one_launch(cin, cout, s, shape):
                 ym, ks = _kernels(lambda: mine(xm, residual=lm))
             out[mode] = (ym.float().cpu(), ks)
     finally:
-        ops.set_pointwise_tma(False)
+        ops.set_pointwise_tma(True)
     assert out[True][1] == [("fprop", "conv_pw_up")] and len(out[False][1]) == st[0] * st[1] * st[2]     # one launch instead of one per tap
     assert rel_err(out[True][0], yr.detach()) < 5e-3
     assert rel_err(out[True][0], out[False][0]) < 2e-3
