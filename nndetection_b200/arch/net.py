@@ -23,6 +23,17 @@ from . import conv_ops as ops
 from .conv_ops import pad32, t3
 
 
+_LEVEL_STREAMS = {}          # per (device, pyramid level); module-level so that the model stays deep-copyable / picklable
+
+
+def level_stream(device, level: int) -> "torch.cuda.Stream":
+    """The side stream of a pyramid level (decoder `out` convolution and detection-head convolutions of the coarse levels)."""
+    key = (str(device), int(level))
+    if key not in _LEVEL_STREAMS:
+        _LEVEL_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _LEVEL_STREAMS[key]
+
+
 # ------------------------------------------------------------------------------------------------ encoder
 class StackedConvBlock2(nn.Module):
     expansion = 2
@@ -157,15 +168,38 @@ class UFPNModular(nn.Module):
     def get_channels(self) -> List[int]:
         return self.out_channels
 
-    def forward(self, inp_seq: Sequence[Tensor]) -> List[Tensor]:
+    def forward(self, inp_seq: Sequence[Tensor], levels: Optional[Sequence[int]] = None,
+                side_levels: Sequence[int] = ()) -> List[Tensor]:
+        """levels: pyramid levels whose `out` convolution is needed (default: all, the reference's protocol).  The detector passes
+        its head levels + level 0 for the segmenter; an `out` map nobody reads (P1 under the LUNA plan) is then not computed -- dead
+        code in the reference too: it has no consumer and receives no gradient.  Skipped levels are `None` in the returned list.
+        side_levels: levels whose `out` convolution runs on that level's side stream (the coarse levels' 30-70 us launches overlap
+        the rest of the top-down path; the consumer -- the detection head -- continues on the same stream)."""
         lat = [self.lateral[f"P{l}"](f) for l, f in enumerate(inp_seq)]
         xs = [None] * self.num_level
         x = lat[-1]
         xs[-1] = x
+        outs = [None] * self.num_level
+        need = set(range(self.num_level)) if levels is None else set(levels)
+        cur = torch.cuda.current_stream(x.device) if x.is_cuda else None
+
+        def out_on_side(l):
+            if l in need and l in side_levels and cur is not None:
+                st = level_stream(x.device, l)
+                st.wait_stream(cur)
+                self.out[f"P{l}"][0].packed()                     # pack on the current stream (no-op when cached)
+                with torch.cuda.stream(st):
+                    outs[l] = self.out[f"P{l}"](xs[l])
+                xs[l].record_stream(st)
+        out_on_side(self.num_level - 1)
         for l in range(self.num_level - 1, 0, -1):
             x = self.up[f"P{l}"](x, residual=lat[l - 1])          # lateral + up, one kernel
             xs[l - 1] = x
-        return [self.out[f"P{l}"](v) for l, v in enumerate(xs)]
+            out_on_side(l - 1)
+        for l, v in enumerate(xs):
+            if l in need and outs[l] is None:
+                outs[l] = self.out[f"P{l}"](v)
+        return outs
 
 
 # ------------------------------------------------------------------------------------------------ heads
@@ -324,6 +358,8 @@ class _HeadOutFn(torch.autograd.Function):
         return (None, dwc, dbc, dwr, dbr, *dscales, *dfc, *dfr)
 
 
+
+
 class DetectionHeadHNMNative(nn.Module):
     """Detection head with hard-negative mining and GIoU on decoded boxes (comb.py:351-405), sync-free."""
 
@@ -334,6 +370,8 @@ class DetectionHeadHNMNative(nn.Module):
         self.n_scales = regressor.num_levels if regressor.learn_scale else 0
         self._packed, self._packed_key, self._plans = None, None, {}
         self.sample_seed = 0
+        self.parallel_levels = True      # coarse pyramid levels on side streams (False: everything on the current stream, A/B)
+        self.pyramid_levels = None       # decoder levels of the feature maps (set by BaseRetinaNet): selects the streams the decoder used
 
     def packed_out(self):
         from .conv import _WEIGHTS_EPOCH
@@ -362,13 +400,42 @@ class DetectionHeadHNMNative(nn.Module):
         return self._plans[key]
 
     def forward(self, fmaps: List[Tensor]) -> Dict[str, Tensor]:
-        fc = [self.classifier.conv_internal(p) for p in fmaps]
-        fr = [self.regressor.conv_internal(p) for p in fmaps]
+        if self.parallel_levels and len(fmaps) > 1 and fmaps[0].is_cuda:
+            fc, fr = self._internal_convs_on_level_streams(fmaps)
+        else:
+            fc = [self.classifier.conv_internal(p) for p in fmaps]
+            fr = [self.regressor.conv_internal(p) for p in fmaps]
         scales = [s.scale for s in self.regressor.scales] if self.n_scales else []
         logits, deltas = _HeadOutFn.apply(self, self.classifier.conv_out.conv.weight, self.classifier.conv_out.conv.bias,
                                           self.regressor.conv_out.conv.weight, self.regressor.conv_out.conv.bias,
                                           *scales, *fc, *fr)
         return {"box_deltas": deltas, "box_logits": logits}
+
+    def _internal_convs_on_level_streams(self, fmaps: List[Tensor]):
+        """The internal convolutions of the coarser pyramid levels (16^3 ... 4^3 at the LUNA plan) are launches of 30-70 us that fill a
+        fraction of the 148 SMs each (64, 16, 4 tiles): level l >= 1 runs on its own side stream, concurrently with the other levels
+        and with level 0 on the current stream.  The levels are independent (weights shared, read-only in forward; their gradient
+        kernels all ADD atomically into the same buffers); autograd runs every node's backward on the stream its forward ran on and
+        orders the streams itself, so the backward pass overlaps the same way."""
+        cur = torch.cuda.current_stream(fmaps[0].device)
+        streams = [level_stream(fmaps[0].device, lv) for lv in self.pyramid_levels[1:len(fmaps)]] if self.pyramid_levels is not None \
+            else [level_stream(fmaps[0].device, 100 + i) for i in range(len(fmaps) - 1)]
+        for m in list(self.classifier.conv_internal) + list(self.regressor.conv_internal):
+            m.packed()                                 # (re-)pack the shared weights ONCE, on the current stream, before any level reads them
+            m.packed_items()
+        fc, fr = [None] * len(fmaps), [None] * len(fmaps)
+        for l in range(1, len(fmaps)):
+            st = streams[l - 1]
+            st.wait_stream(cur)                        # (a feature map produced on this very stream is already in order)
+            with torch.cuda.stream(st):
+                fc[l] = self.classifier.conv_internal(fmaps[l])
+                fr[l] = self.regressor.conv_internal(fmaps[l])
+        fc[0] = self.classifier.conv_internal(fmaps[0])
+        fr[0] = self.regressor.conv_internal(fmaps[0])
+        for l in range(1, len(fmaps)):
+            cur.wait_stream(streams[l - 1])
+            fc[l].record_stream(cur); fr[l].record_stream(cur)      # allocated under a side stream, consumed on the current one
+        return fc, fr
 
     def postprocess_for_inference(self, prediction: Dict[str, Tensor], anchors: List[Tensor]) -> Dict[str, Tensor]:
         """comb.py:140-158: decode all anchors + sigmoid."""

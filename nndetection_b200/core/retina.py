@@ -19,8 +19,8 @@ from .boxes import engine as E
 _SIDE_STREAMS = {}          # per device; kept out of the module so that the model stays deep-copyable / picklable
 
 
-def _side_stream(device) -> torch.cuda.Stream:
-    key = str(device)
+def _side_stream(device, name: str = "targets") -> torch.cuda.Stream:
+    key = (str(device), name)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -87,11 +87,36 @@ class BaseRetinaNet(nn.Module):
 
     # ---------------------------------------------------------------- forward (retina.py:198-226)
     def forward(self, inp: Tensor):
-        features_maps_all = self.decoder(self.encoder(inp))
+        from ..arch.net import UFPNModular
+        lazy = isinstance(self.decoder, UFPNModular)
+        if lazy:
+            # only the decoder outputs somebody reads: the head's levels + level 0 for the segmenter; the coarse head levels' `out`
+            # convolutions run on their level's side stream, where the head continues with them
+            need = set(self.decoder_levels) | ({0} if self.segmenter is not None else set())
+            side = tuple(self.decoder_levels[1:]) if getattr(self.head, "parallel_levels", False) and inp.is_cuda else ()
+            features_maps_all = self.decoder(self.encoder(inp), levels=need, side_levels=side)
+            if hasattr(self.head, "pyramid_levels"):
+                self.head.pyramid_levels = tuple(self.decoder_levels)
+        else:
+            features_maps_all = self.decoder(self.encoder(inp))
         feature_maps_head = [features_maps_all[i] for i in self.decoder_levels]
+        pred_seg = None
+        seg_stream = None
+        if self.segmenter is not None and inp.is_cuda and getattr(self.head, "parallel_levels", False):
+            # the segmentation branch (1x1x1 convolution over the finest map: a streaming, HBM-bound launch) beside the tensor-bound head
+            cur = torch.cuda.current_stream(inp.device)
+            seg_stream = _side_stream(inp.device, "seg")
+            seg_stream.wait_stream(cur)
+            with torch.cuda.stream(seg_stream):
+                pred_seg = self.segmenter(features_maps_all)
         pred_detection = self.head(feature_maps_head)
         anchors = self.anchor_generator(inp, feature_maps_head)
-        pred_seg = self.segmenter(features_maps_all) if self.segmenter is not None else None
+        if seg_stream is not None:
+            torch.cuda.current_stream(inp.device).wait_stream(seg_stream)
+            for v in pred_seg.values():
+                v.record_stream(torch.cuda.current_stream(inp.device))
+        elif self.segmenter is not None:
+            pred_seg = self.segmenter(features_maps_all)
         return pred_detection, anchors, pred_seg
 
     # ---------------------------------------------------------------- training (retina.py:86-159)

@@ -26,13 +26,13 @@
 namespace {
 
 constexpr int PW_BM = 128;
-constexpr int PW_THREADS = 6 * 32;
+constexpr int PW_THREADS = 10 * 32;            // TMA producer, MMA issuer, 2 x 4 epilogue warps
 
 struct PwArgs {
   long long M;                     // rows of A (voxels)
   int K, Ntot, Cout;               // Ntot = taps * Cout columns; tap of column n = n / Cout
   int BN_tiles;                    // Ntot / BN
-  long long m_tiles;
+  int m_tiles;
   // output mapping: row m = ((n * D + z) * H + y) * W + x  ->  voxel ((n * Do + z*omd + od) * Ho + y*omh + oh) * Wo + x*omw + ow
   int D, H, W, Do, Ho, Wo, omd, omh, omw;
   int identity;                    // output voxel == m (no decode needed)
@@ -64,28 +64,36 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int ROWB = BK * 2;                              // bytes per operand row in a slot = swizzle span
   constexpr int A_BYTES = PW_BM * ROWB, B_BYTES = BN * ROWB;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : (2 * BN >= 128 ? 128 : 64));
+  // accumulator stages: the chain MMA -> commit -> epilogue wake-up -> tcgen05.ld -> stores -> TEMPTY -> next MMA costs ~2000 cycles per
+  // stage (ncu of the 2-stage version: the epilogue warps polled TFULL 4x per tile), HBM needs ~700 per 128 x 32 tile: 8 stages hide it
+  constexpr int ACC = 512 / BN > 8 ? 8 : 512 / BN;
+  constexpr int TMEM_COLS = ACC * BN >= 512 ? 512 : (ACC * BN >= 256 ? 256 : (ACC * BN >= 128 ? 128 : 64));
   constexpr unsigned IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "swizzled slots need 1024-byte alignment");
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the dynamic segment is only guaranteed 16-byte alignment: round up by hand (the launcher allocates 1 KB of slack)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ unsigned long long bars[2 * STAGES + 4];
+  __shared__ unsigned long long bars[2 * STAGES + 2 * ACC];
   __shared__ unsigned s_tmem_base;
+  __shared__ float s_bias[1024];                            // [Cout] (zeros without a bias)
+  __shared__ int s_tapoff[8];                               // output-voxel offset of a tap: (od * Ho + oh) * Wo + ow
+  __shared__ uint4 s_stage[8][128];                         // per epilogue warp: 32 rows x 64 bytes, transposition buffer
   const unsigned bar0 = smem_u32(bars);
   auto FULL = [&](int i) { return bar0 + 8u * i; };
   auto EMPTY = [&](int i) { return bar0 + 8u * (STAGES + i); };
   auto TFULL = [&](int i) { return bar0 + 8u * (2 * STAGES + i); };
-  auto TEMPTY = [&](int i) { return bar0 + 8u * (2 * STAGES + 2 + i); };
+  auto TEMPTY = [&](int i) { return bar0 + 8u * (2 * STAGES + ACC + i); };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KB = a.K / BK;
-  const long long total = a.m_tiles * a.BN_tiles;
+  const int total = a.m_tiles * a.BN_tiles;                 // < 2^31 (host check)
 
+  for (int i = tid; i < a.Cout; i += PW_THREADS) s_bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (tid < 8) s_tapoff[tid] = (a.od[tid] * a.Ho + a.oh[tid]) * a.Wo + a.ow[tid];
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), 4); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(TFULL(i), 1); mbar_init(TEMPTY(i), BN == 32 ? 4 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -101,13 +109,13 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================================================ TMA producer
     if (lane == 0) {
       unsigned stage = 0, phase = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const long long mb = tile / a.BN_tiles; const int nb = (int)(tile % a.BN_tiles);
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int mb = tile / a.BN_tiles, nb = tile - mb * a.BN_tiles;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(EMPTY(stage), phase ^ 1);
           const unsigned sa = smem_u32(smem + stage * STAGE_BYTES);
           pw_expect_tx(FULL(stage), STAGE_BYTES);
-          pw_tma_2d(sa, &map_a, kb * BK, (int)(mb * PW_BM), FULL(stage));
+          pw_tma_2d(sa, &map_a, kb * BK, mb * PW_BM, FULL(stage));
           pw_tma_2d(sa + A_BYTES, &map_w, kb * BK, nb * BN, FULL(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -117,7 +125,7 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================================================ MMA issuer
     if (lane == 0) {
       unsigned stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         mbar_wait(TEMPTY(acc), acc_phase ^ 1);
         tc_fence_after();
         const unsigned d_tmem = tmem_base + acc * BN;
@@ -133,69 +141,107 @@ conv_pw_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(TFULL(acc));
-        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ================================================================ epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
+    // ================================================================ epilogue: two groups of four warps (TMEM lane quarter = warp % 4).
+    // The per-tile chain TFULL wait -> tcgen05.ld -> convert -> stores is latency-, not throughput-bound (ncu of the first version: one
+    // group needed ~1200 cycles per 128 x 32 tile against ~690 cycles of HBM time), so two groups work concurrently: single-chunk tiles
+    // (BN = 32) alternate between the groups (group g owns accumulator stage g), wider tiles split their 32-column chunks by parity.
+    constexpr int CH = BN / 32;
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    unsigned acc = 0, acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const long long mb = tile / a.BN_tiles; const int nb = (int)(tile % a.BN_tiles);
-      const long long m = mb * PW_BM + row;
+    const unsigned cout = (unsigned)a.Cout;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++local) {
+      if (CH == 1 && (local & 1) != grp) continue;
+      const unsigned acc = (unsigned)(local % ACC), acc_phase = (unsigned)((local / ACC) & 1);
+      const int mb = tile / a.BN_tiles, nb = tile - mb * a.BN_tiles;
+      const long long m = (long long)mb * PW_BM + row;
       const bool ok = m < a.M;
-      long long vbase = m;                                    // output voxel of tap offset (0, 0, 0)
-      int zc = 0, yc = 0, xc = 0; long long nn = 0;
+      unsigned vbase0 = (unsigned)m;                           // output voxel of tap offset (0, 0, 0); voxel counts fit 32 bits (host check)
       if (!a.identity && ok) {
-        long long t = m;
-        xc = (int)(t % a.W); t /= a.W; yc = (int)(t % a.H); t /= a.H; zc = (int)(t % a.D); nn = t / a.D;
+        unsigned t = (unsigned)m;
+        const unsigned xc = t % (unsigned)a.W; t /= (unsigned)a.W;
+        const unsigned yc = t % (unsigned)a.H; t /= (unsigned)a.H;
+        const unsigned zc = t % (unsigned)a.D; const unsigned nn = t / (unsigned)a.D;
+        vbase0 = ((nn * a.Do + zc * a.omd) * a.Ho + yc * a.omh) * a.Wo + xc * a.omw;
       }
+      auto out_offset = [&](int c, unsigned& co0) -> long long {
+        const unsigned n0 = (unsigned)(nb * BN + c * 32);
+        const unsigned tap = a.identity ? 0u : n0 / cout;
+        co0 = n0 - tap * cout;
+        return (long long)(vbase0 + (unsigned)s_tapoff[tap]) * cout + co0;
+      };
+      const int c_first = CH == 1 ? 0 : grp;
       mbar_wait_warp(TFULL(acc), acc_phase, lane);
       tc_fence_after();
+      // Global accesses of a chunk (64 bytes per row) go through a per-warp 2 KB transposition buffer: a lane OWNS one row (its
+      // TMEM lane), but instruction u of a warp-wide 16-byte access covers rows 8u .. 8u+7 with FOUR LANES PER ROW (lane l -> row
+      // 8u + l/4, piece l%4), i.e. whole 32-byte sectors / 64-byte chunks per row.  (The first version let every lane store its own row:
+      // 32 half-written sectors per instruction -- ncu: 33.5 M sector writes for 16.8 M sectors of output, the L1 store path at ~0.5
+      // sectors/clk was the kernel's limiter at 50 % of the HBM peak.)  Buffer slot of (row r, piece p): r*4 + (p ^ ((r >> 1) & 3)).
+      uint4* stg = s_stage[warp - 2];
+      const int sub_row = lane >> 2, piece = lane & 3;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_first; c < CH; c += (CH == 1 ? 1 : 2)) {
         unsigned v[32];
-        tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + c * 32, v);
-        const int n0 = nb * BN + c * 32;
-        const int tap = n0 / a.Cout, co0 = n0 - tap * a.Cout;
-        if (!a.identity)
-          vbase = ((nn * a.Do + zc * a.omd + a.od[tap]) * a.Ho + yc * a.omh + a.oh[tap]) * a.Wo + xc * a.omw + a.ow[tap];
+        tmem_ld32_issue(tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + c * 32, v);
+        unsigned co0;
+        const long long o = out_offset(c, co0);                 // this lane's row
+        long long o_r[4]; bool ok_r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          o_r[u] = __shfl_sync(0xffffffffu, o, u * 8 + sub_row);
+          ok_r[u] = __shfl_sync(0xffffffffu, (int)ok, u * 8 + sub_row) != 0;
+        }
+        uint4 rr[4];
+        if (a.residual) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            rr[u] = ok_r[u] ? *reinterpret_cast<const uint4*>(a.residual + o_r[u] + piece * 8) : make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (a.bias) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[co0 + j];
+        if (a.residual) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += a.bias[co0 + j];
-        }
-        if (ok) {
-          const long long o = vbase * a.Cout + co0;
-          if (a.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + o);
+          for (int u = 0; u < 4; ++u) { const int r = u * 8 + sub_row; stg[r * 4 + (piece ^ ((r >> 1) & 3))] = rr[u]; }
+          __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint4 rv = rp[u];
-              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          for (int u = 0; u < 4; ++u) {
+            const uint4 rv = stg[lane * 4 + (u ^ ((lane >> 1) & 3))];
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 t2 = __bfloat1622float2(hp[k]);
-                f[u * 8 + 2 * k] += t2.x; f[u * 8 + 2 * k + 1] += t2.y;
-              }
+            for (int k = 0; k < 4; ++k) {
+              const float2 t2 = __bfloat1622float2(hp[k]);
+              f[u * 8 + 2 * k] += t2.x; f[u * 8 + 2 * k + 1] += t2.y;
             }
           }
-          __align__(16) __nv_bfloat162 pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          uint4* op = reinterpret_cast<uint4*>(a.out + o);
-          const uint4* sp = reinterpret_cast<const uint4*>(pk);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) op[u] = sp[u];
+          __syncwarp();
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint4 pv;
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pv);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(f[u * 8 + 2 * k], f[u * 8 + 2 * k + 1]);
+          stg[lane * 4 + (u ^ ((lane >> 1) & 3))] = pv;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = u * 8 + sub_row;
+          if (ok_r[u]) *reinterpret_cast<uint4*>(a.out + o_r[u] + piece * 8) = stg[r * 4 + (piece ^ ((r >> 1) & 3))];
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -241,13 +287,14 @@ int launch_pw(const __nv_bfloat16* x, const __nv_bfloat16* w, PwArgs a, cudaStre
   if (make_map(&map_a, x, a.M, a.K, PW_BM, BK) != NND_OK || make_map(&map_w, w, a.Ntot, a.K, BN, BK) != NND_OK)
     return nnd_set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
   a.BN_tiles = a.Ntot / BN;
-  a.m_tiles = (a.M + PW_BM - 1) / PW_BM;
+  a.m_tiles = (int)((a.M + PW_BM - 1) / PW_BM);
+  if ((long long)a.m_tiles * a.BN_tiles >= (1ll << 31) || a.Cout > 1024) return NND_ERR_ARG;
   constexpr size_t SMEM = (size_t)STAGES * (PW_BM + BN) * BK * 2 + 1024;
   static NndPerDeviceOnce attr_set;
   if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_pw_kernel<BN, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   }
-  const long long total = a.m_tiles * a.BN_tiles;
+  const long long total = (long long)a.m_tiles * a.BN_tiles;
   const int grid = total < NND_NUM_SMS ? (int)total : NND_NUM_SMS;
   conv_pw_kernel<BN, BK, STAGES><<<grid, PW_THREADS, SMEM, st>>>(map_a, map_w, a);
   NND_LAUNCH_CHECK("conv_pw_kernel");

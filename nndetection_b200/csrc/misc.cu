@@ -150,6 +150,32 @@ __global__ void scale_grad_kernel(const float* __restrict__ g, const float* __re
   }
 }
 
+// same reduction, 16-byte loads, one grid row per sample (no per-element division): the dense gradient it scans is zero except for
+// the <= max_pos sampled anchors, so the launch is a pure streaming read of g (85 MB at the 32^3 level of the LUNA plan)
+__global__ void __launch_bounds__(256)
+scale_grad_vec_kernel(const float4* __restrict__ g, const float4* __restrict__ out, long long len4, long long n_stride4,
+                      const float* __restrict__ scale, float* __restrict__ dscale) {
+  __shared__ float sh[8];
+  const float4* gn = g + (long long)blockIdx.y * n_stride4;
+  const float4* on = out + (long long)blockIdx.y * n_stride4;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gv = gn[i];
+    if (gv.x != 0.f || gv.y != 0.f || gv.z != 0.f || gv.w != 0.f) {
+      const float4 ov = on[i];
+      acc += gv.x * ov.x + gv.y * ov.y + gv.z * ov.z + gv.w * ov.w;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float r = threadIdx.x < 8 ? sh[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+    if (threadIdx.x == 0 && r != 0.f) atomicAdd(dscale, r / *scale);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -222,7 +248,15 @@ int nnd_cast_f32_bf16(const float* s, void* d, long long n, cudaStream_t st) {
 int nnd_scale_grad(const float* g, const float* out, int N, long long len, long long n_stride, const float* scale, float* dscale,
                    cudaStream_t st) {
   if ((long long)N * len <= 0) return NND_OK;
-  scale_grad_kernel<<<NND_NUM_SMS, 256, 0, st>>>(g, out, N, len, n_stride, scale, dscale);
+  if (len % 4 == 0 && n_stride % 4 == 0 && (((size_t)g | (size_t)out) & 15) == 0) {
+    const long long len4 = len / 4;
+    long long bx = (len4 + 256 * 8 - 1) / (256 * 8);                 // ~8 float4 per thread
+    if (bx > 4 * NND_NUM_SMS) bx = 4 * NND_NUM_SMS;
+    if (bx < 1) bx = 1;
+    scale_grad_vec_kernel<<<dim3((unsigned)bx, (unsigned)N), 256, 0, st>>>((const float4*)g, (const float4*)out, len4, n_stride / 4, scale, dscale);
+  } else {
+    scale_grad_kernel<<<NND_NUM_SMS, 256, 0, st>>>(g, out, N, len, n_stride, scale, dscale);
+  }
   NND_LAUNCH_CHECK("scale_grad_kernel");
   return NND_OK;
 }
