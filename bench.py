@@ -204,6 +204,8 @@ def main():
         conv_ops.set_pointwise_tma(True)
     if "no_pw_tma" in args.experimental.split(","):
         conv_ops.set_pointwise_tma(False)
+    if "tcs_map" in args.experimental.split(","):            # A/B: coalesced halo copy mapping in the streaming kernel
+        L.lib().nnd_conv_set_tcs_map(1)
     if "tc_bulk" in args.experimental.split(","):
         conv_ops.set_tc_bulk(True)
     if "norm_narrow" in args.experimental.split(","):

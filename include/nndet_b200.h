@@ -126,6 +126,7 @@ void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_wgrad_strided_tc(int enable);       /* default 1 (validated on B200, round 2): de-interleaved tcgen05 wgrad for stride-2 / transposed convolutions; 0 = mma.sync (A/B) */
 void nnd_conv_set_gather_strided_tc(int enable);      /* default 1 (validated on B200, round 2): de-interleaved-halo tcgen05 kernel for stride-2 gathers; 0 = mma.sync (A/B) */
+void nnd_conv_set_tcs_map(int mode);                  /* A/B switch: halo copy lane mapping of the streaming kernel (0 row-walking threads, 1 lanes along a voxel's channel groups) */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
 /* Profiling aid (off by default): one row per convolution-family launch -- kind (fprop | wgrad | first_*), the kernel the dispatch
  * chose, the geometry, and the launch's duration from two CUDA events on its stream.  trace(1) clears + starts, trace(0) stops;

@@ -36,6 +36,7 @@ struct TcsTiles {
   int ZS, NZ, HB, WB, NT;      // z-segment length, segments per column, tiles along h / w, 32-channel output tiles
   int per_nt;                  // work items per output tile = N * NZ * HB * WB
   int total;                   // per_nt * NT
+  int map_mode;                // halo copy lane mapping: 0 one thread per (group, y) row, 1 lanes along the channel groups of a voxel
 };
 
 struct Item { int n, z0, z1, h0, w0, nt; };
@@ -144,6 +145,19 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
       for (int s = s_lo; s <= s_hi; ++s) {
         mbar_wait_warp(HEMPTY(slot), phase ^ 1, lane);
         const unsigned a_base = smem_u32(sA + slot * SLOT_BYTES);
+        if (tl.map_mode == 1) {
+          // lanes = the KG consecutive 16-byte channel groups of one voxel, then the next voxel of the row: a warp instruction reads
+          // ~512 contiguous bytes (4-5 lines) instead of 32 different lines -- the LSU processes one line per cycle, and the round-1
+          // mapping (one thread per (group, y) row walking x) spent ~720 of the ~1000 cycles an input slice's MMAs take on them
+          const __nv_bfloat16* slice = in_n + (long long)s * g.Hi * g.Wi * g.Cin;
+          for (int c = tid; c < HY * HX * KG; c += NPROD) {
+            const int kg = c % KG; const int t = c / KG;
+            const int x = t % HX, y = t / HX;
+            const int h = it.h0 - 1 + y, w = it.w0 - 1 + x;
+            const bool ok = (unsigned)h < (unsigned)g.Hi && (unsigned)w < (unsigned)g.Wi;
+            cp_async16(a_base + kg * GP + y * ROW_PITCH + x * 16, ok ? slice + ((long long)h * g.Wi + w) * g.Cin + kg * 8 : in, ok);
+          }
+        } else {
         for (int rr = tid; rr < KG * HY; rr += NPROD) {
           const int kg = rr / HY, y = rr - kg * HY;
           const int h = it.h0 - 1 + y;
@@ -156,6 +170,7 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
             cp_async16(dst, ok ? src : in, ok);
             dst += 16; src += g.Cin;
           }
+        }
         }
         cp_async_commit();
         ++pending;
@@ -334,6 +349,7 @@ conv_tcs_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __res
 }
 
 int g_tcs_issuers = 2;
+int g_tcs_map = 0;             // halo copy lane mapping (TcsTiles::map_mode); nnd_conv_set_tcs_map
 
 template <int CIN, int NI, int A_SLOTS, int LAG, bool STATS>
 int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
@@ -353,6 +369,7 @@ int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
   tl.ZS = best_zs; tl.NZ = (g.Ld + tl.ZS - 1) / tl.ZS;
   tl.per_nt = g.N * tl.NZ * tl.HB * tl.WB;
   tl.total = tl.per_nt * tl.NT;
+  tl.map_mode = g_tcs_map;
   constexpr size_t SMEM = (size_t)9 * (CIN / 8) * WROW + (size_t)A_SLOTS * (CIN / 8) * GP + 8 * (2 * A_SLOTS + 2 * ACC_SLOTS);
   static NndPerDeviceOnce attr_set;
   if (attr_set.need()) {
@@ -367,6 +384,8 @@ int launch_tcs(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
 }  // namespace
 
 void nnd_conv_tcs_set_issuers(int n) { g_tcs_issuers = n == 1 ? 1 : 2; }
+// halo copy lane mapping of the streaming kernel: 0 = one thread per (channel group, y) row, 1 = lanes along the channel groups of a voxel
+extern "C" void nnd_conv_set_tcs_map(int mode) { g_tcs_map = mode ? 1 : 0; }
 
 int nnd_conv_tcs_supported(const ConvGeom& g, const ConvEpilogue& ep) {
   if (g.sd != 1 || g.sh != 1 || g.sw != 1) return 0;

@@ -21,6 +21,10 @@ if os.environ.get("NND_TC_RING"):
     from nndetection_b200 import _lib as L2
     from ctypes import c_int as _ci
     L2.lib().nnd_conv_set_tc_ring(_ci(int(os.environ["NND_TC_RING"])))
+if os.environ.get("NND_TCS_MAP"):
+    from nndetection_b200 import _lib as L3
+    from ctypes import c_int as _ci3
+    L3.lib().nnd_conv_set_tcs_map(_ci3(int(os.environ["NND_TCS_MAP"])))
 stride = int(os.environ.get("NND_STRIDE", "1"))
 if os.environ.get("NND_S2") == "0":          # A/B: strided forms on the mma.sync kernels
     ops.set_gather_strided_tc(False)

@@ -16,6 +16,10 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        if os.environ.get("NND_TCS_MAP"):          # A/B runs of the whole suite with the streaming kernel's other halo copy mapping
+            from ctypes import c_int
+            from nndetection_b200 import _lib as L
+            L.lib().nnd_conv_set_tcs_map(c_int(int(os.environ["NND_TCS_MAP"])))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

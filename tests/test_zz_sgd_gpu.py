@@ -46,7 +46,7 @@ def test_parameters_without_a_gradient_are_left_alone_like_torch_sgd_does():
     from nndetection_b200.ptmodule import RetinaUNetV001
     from nndetection_b200.training import Trainer
     arch, anc, patch, bs = make_plan("tiny")
-    arch = dict(arch, decoder_levels=(2,))                       # P0 -> segmenter, P1 -> nothing, P2 -> detection head
+    arch = dict(arch, decoder_levels=(2,), fpn_channels=128, head_channels=128)   # P0 (32 ch) -> segmenter, P1 (64) -> nothing, P2 (128) -> head
     anc = {k: v[:1] for k, v in anc.items()}
     torch.manual_seed(1)
     net = RetinaUNetV001.from_config_plan(None, arch, anc).cuda()
