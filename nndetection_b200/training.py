@@ -143,6 +143,7 @@ class GradientBuckets:
         self.pending = list(self.static_pending)
         self.launched = [False] * len(self.bounds)
         self.works, self.order, self.in_backward = [], [], False
+        self.main_stream = torch.cuda.current_stream(self.fp.grad.device) if self.fp.grad.is_cuda else None
 
     # ---- observer protocol of arch/conv.py
     def layer_used(self, layer):
@@ -166,6 +167,16 @@ class GradientBuckets:
         lo, hi = self.bounds[b]
         self.launched[b] = True
         self.order.append(b)
+        # The bucket's gradients were written by kernels on the stream each layer's forward ran on (the coarse pyramid levels and the
+        # segmentation branch have side streams, arch/net.py / core/retina.py); the collective orders itself after the CURRENT stream
+        # only, so join the side streams first.
+        if self.fp.grad.is_cuda:
+            from .arch.net import _LEVEL_STREAMS
+            from .core.retina import _SIDE_STREAMS
+            cur = torch.cuda.current_stream(self.fp.grad.device)
+            for st in list(_LEVEL_STREAMS.values()) + list(_SIDE_STREAMS.values()) + [self.main_stream]:
+                if st is not None and st.device == self.fp.grad.device and st != cur:
+                    cur.wait_stream(st)
         self.works.append(dist.all_reduce(self.fp.grad[lo:hi], async_op=True))
 
     def finish(self):
