@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="timed region only (for ncu): no e2e / roofline / cpu baseline")
     ap.add_argument("--igemm-only", action="store_true", help="disable the tcgen05 conv kernel (A/B)")
-    ap.add_argument("--experimental", default="", help="comma list of A/B switches: mma_s2 (strided / transposed forms on the mma.sync kernels instead of tcgen05), tc_bulk (tile kernel weights via cp.async.bulk: deadlocks, do not use), norm_narrow (4-channel norm backward passes), buckets (N > 1: 25 MB gradient buckets all-reduced during backward)")
+    ap.add_argument("--experimental", default="", help="comma list of A/B switches: mma_s2 (strided / transposed forms on the mma.sync kernels instead of tcgen05), tc_bulk (tile kernel weights via cp.async.bulk: deadlocks, do not use), norm_narrow (4-channel norm backward passes), no_buckets (N > 1: ONE all-reduce of the flat gradient after backward instead of 25 MB buckets all-reduced during it), no_streams (coarse pyramid levels on the main stream), tcs_map, no_pw_tma")
     ap.add_argument("--stock-tuned", action="store_true", help="internal: only the tuned stock-PyTorch comparator (cudnn.benchmark + channels_last_3d), one JSON line")
     ap.add_argument("--trace-layers", default=None, metavar="CSV",
                     help="after the timed regions run ONE extra step with the per-launch convolution trace on and write it here "
@@ -213,7 +213,9 @@ def main():
     arch, anc, patch, bs = make_plan(args.config)
     torch.manual_seed(1234 + rank)
     net = RetinaUNetV001.from_config_plan(None, arch, anc).to(dev)
-    trainer = Trainer(net, distributed=world > 1, bucket_mb=25.0 if "buckets" in args.experimental.split(",") else None)
+    if "no_streams" in args.experimental.split(","):          # A/B: coarse pyramid levels / segmentation branch on the main stream
+        net.head.parallel_levels = False
+    trainer = Trainer(net, distributed=world > 1, bucket_mb=None if "no_buckets" in args.experimental.split(",") else 25.0)
 
     # ---- synthetic data: 4 distinct batches (> L2: one batch of activations alone is GBs), pinned on the host
     # as many distinct batches as warm-up steps (<= 4): every batch's allocation pattern (it depends on the number of ground-truth
