@@ -261,11 +261,13 @@ int launch_wt(WtArgs a, int co_pad, int ci_pad, cudaStream_t st) {
 int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx) {
   if (g.sd != 1 || g.sh != 1 || g.sw != 1 || g.omd != 1 || g.omh != 1 || g.omw != 1 || g.ood || g.ooh || g.oow) return 0;
   if (g.Ld != g.Di || g.Lh != g.Hi || g.Lw != g.Wi || g.Do != g.Di || g.Ho != g.Hi || g.Wo != g.Wi) return 0;
-  // 3x3x3 / 1x3x3 filters, or the single tap of a 1x1x1 convolution (laterals: one filter-row group, only the centre issuer works;
-  // the launch is bound by reading dy and x once from HBM, so the idle MMA rows of a 32-channel dy cost nothing there)
+  // 3x3x3 / 1x3x3 filters, or the single tap of a 1x1x1 convolution with >= 64 output channels (laterals: one filter-row group, only
+  // the centre issuer works)
   const bool pointwise = g.T == 1 && g.off_d[0] == 0 && g.off_h[0] == 0 && g.off_w[0] == 0;
   if ((g.T < 9 && !pointwise) || Cdy % 32 || Cx % 32) return 0;
-  if (!pointwise && Cdy < 64) return 0;                             // 32-channel dy would fill a quarter of the 128-row MMA
+  // 32-channel dy fills a quarter of the 128-row MMA; for the pointwise form its 64-voxel pipeline stages are also far too small
+  // (measured: 32->32 @128^3 0.87 ms here against 0.47 ms on the mma.sync kernel, 64->64 @64^3 0.13 against 0.15)
+  if (Cdy < 64) return 0;
   for (int t = 0; t < g.T; ++t)
     if (g.off_d[t] < -1 || g.off_d[t] > 1 || g.off_h[t] < -1 || g.off_h[t] > 1 || g.off_w[t] < -1 || g.off_w[t] > 1) return 0;
   return 1;
