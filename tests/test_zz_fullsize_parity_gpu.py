@@ -106,3 +106,41 @@ def test_seg_loss_forward_backward_vs_oracle_autograd(shape, frac):
         assert abs(float(dice) - float(o["seg_dice"])) <= 1e-4 * abs(float(o["seg_dice"])) + 1e-7
         assert rel_err(ld.grad, lo.grad) < 1e-4, (w_ce, w_dice)
         torch.testing.assert_close(ld.grad.cpu(), lo.grad, rtol=1e-3, atol=1e-7 * float(lo.grad.abs().max()) + 1e-9)
+
+
+def test_inference_patch_160_against_the_oracle():
+    """BASELINE config 4's patch (160^3, A = 1 974 375 anchors): `inference_step` on the device against the oracle -- network outputs
+    <= 5e-2 in norm against the fp32 CPU forward, and the whole post-processing (decode + clip + sigmoid + top-10 000 + score / size
+    filters + 3-D NMS + top-100: nndet/core/retina.py:292-379) BIT-EXACT against the oracle's restatement applied to the device's own
+    logits / deltas (boxes within one ulp of expf)."""
+    from nndetection_b200.configs import make_plan
+    from nndetection_b200.ptmodule import RetinaUNetV001
+    arch, anc, patch, _ = make_plan("infer160")
+    torch.manual_seed(160)
+    net = RetinaUNetV001.from_config_plan(None, arch, anc)
+    orc = mo.RetinaUNetOracle(dict(arch), dict(anc))
+    orc.load_state_dict({k: v.detach().clone() for k, v in net.state_dict().items()})
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    images = torch.rand(1, 1, *patch, generator=g)
+    with torch.no_grad():
+        pdet, anchors, pseg = net(images.cuda())
+        pred = net.postprocess_for_inference(images=images.cuda(), pred_detection=pdet, pred_seg=pseg, anchors=anchors)
+        po, anchors_o, so = orc(images)
+    A = anchors_o[0].shape[0]
+    assert A == 1974375 and torch.equal(anchors[0].cpu(), anchors_o[0])
+    assert rel_err(pdet["box_logits"], po["box_logits"]) < 5e-2
+    assert rel_err(pdet["box_deltas"], po["box_deltas"]) < 5e-2
+    assert rel_err(pseg["seg_logits"], so["seg_logits"]) < 5e-2
+    # decode + sigmoid on the device against torch on the same raw outputs (expf ulp), then the oracle's selection / filters / NMS on
+    # the DEVICE's decoded boxes and probabilities -- the same ordering problem, so bit-exact
+    from nndetection_b200.core.boxes import engine as E
+    boxes_d = E.decode_boxes(pdet["box_deltas"], anchors[0], clip_shape=patch)
+    probs_d = E.sigmoid_fg(pdet["box_logits"], want_fg=False)[0]
+    torch.testing.assert_close(probs_d.cpu(), torch.sigmoid(pdet["box_logits"].cpu()), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(boxes_d.cpu(), bo.clip_boxes_3d(bo.decode_single(pdet["box_deltas"].cpu(), anchors_o[0]), patch), rtol=1e-5, atol=1e-3)
+    rb, rs, rl = bo.postprocess_single_image(boxes_d.cpu(), probs_d.cpu(), patch, arch["classifier_classes"], topk=10000, score_thresh=0,
+                                             min_size=0.01, nms_thresh=net.nms_thresh, detections_per_img=100)
+    b, s, l = pred["pred_boxes"][0].cpu(), pred["pred_scores"][0].cpu(), pred["pred_labels"][0].cpu()
+    assert b.shape == rb.shape and b.shape[0] > 0
+    assert torch.equal(l, rl) and torch.equal(s, rs) and torch.equal(b, rb)
