@@ -204,6 +204,8 @@ def main():
         conv_ops.set_pointwise_tma(True)
     if "no_pw_tma" in args.experimental.split(","):
         conv_ops.set_pointwise_tma(False)
+    if "no_wgrad_tma" in args.experimental.split(","):        # A/B: >= 64-channel stride-1 weight gradients back on the cp.async kernel
+        conv_ops.set_wgrad_tma(0)
     if "tcs_map" in args.experimental.split(","):            # A/B: coalesced halo copy mapping in the streaming kernel
         L.lib().nnd_conv_set_tcs_map(1)
     if "tc_bulk" in args.experimental.split(","):

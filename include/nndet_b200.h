@@ -125,6 +125,7 @@ int nnd_detect_postprocess(const float* boxes, const float* probs, int B, long l
 void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_wgrad_strided_tc(int enable);       /* default 1 (validated on B200, round 2): de-interleaved tcgen05 wgrad for stride-2 / transposed convolutions; 0 = mma.sync (A/B) */
+void nnd_conv_set_wgrad_tma(int mode);                /* TMA-fed tcgen05 wgrad (csrc/conv_wgrad_tma.cu) for stride-1 3x3x3 / 1x3x3 layers with channels in multiples of 64: bit 0 on, bit 1 base_offset descriptors (WRONG results: the device-verified model is base_offset 0), bit 2 unstacked taps, bits 3-5 timing experiments, bit 6 ignore the workspace (A/B) */
 void nnd_conv_set_gather_strided_tc(int enable);      /* default 1 (validated on B200, round 2): de-interleaved-halo tcgen05 kernel for stride-2 gathers; 0 = mma.sync (A/B) */
 void nnd_conv_set_tcs_map(int mode);                  /* A/B switch: halo copy lane mapping of the streaming kernel (0 row-walking threads, 1 lanes along a voxel's channel groups) */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
@@ -155,6 +156,12 @@ int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom_ho
 /* dW[co*s_co + ci*s_ci + tap*s_tap] += sum_voxels dy[.., co] * x[.., ci]   (fp32, caller zero-fills) */
 int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom_host, float* dw, long long s_co,
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t stream);
+/* Same launch with an optional workspace (nnd_conv_wgrad_workspace_bytes, host-only query; 0 = none needed): the TMA-fed kernel then
+ * stores its split-K partials with plain 16-byte stores and a finishing pass adds their sum into dw -- taps x Cout x Cin atomics per
+ * launch instead of splits x as many.  ws null / too small: the atomics path. */
+long long nnd_conv_wgrad_workspace_bytes(const int* geom_host, int Cdy, int Cx, int Cout, int Cin);
+int nnd_conv_wgrad_bf16_ws(const void* dy, int Cdy, const void* x, int Cx, const int* geom_host, float* dw, long long s_co,
+                           long long s_ci, long long s_tap, int Cout, int Cin, void* ws, long long ws_bytes, cudaStream_t stream);
 /* image-input layer (Cin <= 4): x fp32 NCDHW, w fp32 [Cout][Cin][T] */
 int nnd_conv_first_fprop_f32(const float* x, const float* w, const int* geom_host, int Cout, void* out, float* stat_sum,
                              float* stat_sq, cudaStream_t stream);

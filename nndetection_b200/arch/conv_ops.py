@@ -168,9 +168,14 @@ def tc_bulk_enabled() -> bool:
 
 def conv_wgrad(dy: Tensor, cdy: int, x: Tensor, cx: int, geom, dw: Tensor, s_co: int, s_ci: int, s_tap: int, cout: int,
                cin: int):
-    L.check(L.lib().nnd_conv_wgrad_bf16(L.ptr(dy), c_int(cdy), L.ptr(x), c_int(cx), geom, L.ptr(dw), c_longlong(s_co),
-                                        c_longlong(s_ci), c_longlong(s_tap), c_int(cout), c_int(cin), L.stream_ptr()),
-            "nnd_conv_wgrad_bf16")
+    lib = L.lib()
+    lib.nnd_conv_wgrad_workspace_bytes.restype = c_longlong
+    nbytes = int(lib.nnd_conv_wgrad_workspace_bytes(geom, c_int(cdy), c_int(cx), c_int(cout), c_int(cin)))
+    # split-K partials of the TMA-fed kernel: from the caching allocator on the launch stream (freed behind the launch in stream order)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device) if nbytes > 0 else None
+    L.check(lib.nnd_conv_wgrad_bf16_ws(L.ptr(dy), c_int(cdy), L.ptr(x), c_int(cx), geom, L.ptr(dw), c_longlong(s_co),
+                                       c_longlong(s_ci), c_longlong(s_tap), c_int(cout), c_int(cin), L.ptr(ws), c_longlong(nbytes),
+                                       L.stream_ptr()), "nnd_conv_wgrad_bf16_ws")
 
 
 def conv_first_fprop(x: Tensor, w: Tensor, geom, cout: int, out: Tensor, stat_sum, stat_sq):
@@ -245,6 +250,15 @@ def set_wgrad_strided_tc(enable: bool):
 def set_gather_strided_tc(enable: bool):
     """De-interleaved-halo tcgen05 kernel for stride-2 convolutions and the dgrad of up-convolutions (default on; False = mma.sync)."""
     L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
+
+
+WGRAD_TMA_DEFAULT = 1      # on since its validation on a B200 (round 2); the C side has the same default
+
+
+def set_wgrad_tma(mode: int):
+    """TMA-fed tcgen05 weight gradient (csrc/conv_wgrad_tma.cu) for stride-1 3x3x3 / 1x3x3 layers with channel counts in multiples of
+    64.  bit 0: on; bit 1: shared-memory descriptors carry base_offset for row-shifted starts; bit 2: one MMA per dx tap (A/B)."""
+    L.lib().nnd_conv_set_wgrad_tma(c_int(int(mode)))
 
 
 _PW_TMA = True           # default since its validation on a B200 (round 2); the C side has the same default

@@ -30,6 +30,11 @@ int nnd_conv_wgrad_tc_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc_strided_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                       long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st);
+int nnd_conv_wgrad_tma_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tma(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                       long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
+                       cudaStream_t st);
+long long nnd_conv_wgrad_tma_workspace(const ConvGeom& g, int Cdy, int Cx, int Cout, int Cin);
 int nnd_conv_wgrad_tc32_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc32_profitable(const ConvGeom& g);
 int nnd_conv_wgrad_tc32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ConvGeom& g, float* dw, long long s_co, long long s_ci,
@@ -66,6 +71,7 @@ int g_stream = 1;
 int g_wgrad_strided = 1;      // validated on a B200 in round 2 (tests/test_strided_tcgen05_gpu.py), default since
 int g_gather_strided = 1;
 int g_tc_bulk = 0;
+int g_wgrad_tma = 1;          // TMA-fed tcgen05 wgrad (conv_wgrad_tma.cu; validated on a B200 in round 2): bit 0 on, bits 1-5 A/B and timing variants
 int g_pw = 1;                 // TMA-fed pointwise GEMM (conv_pw.cu) for single-tap gathers (validated on a B200 in round 2; 0 = A/B)
 
 // ---- per-launch trace (profiling aid, off by default): which kernel served which layer shape and how long it ran.
@@ -119,6 +125,10 @@ void nnd_conv_set_tc_bulk(int enable) { g_tc_bulk = enable; }
 // 1: single-tap gathers (1x1x1 convolutions and their dgrad, parity classes of up-convolutions) take the TMA-fed tcgen05 GEMM of
 // conv_pw.cu instead of the mma.sync gather kernel.
 void nnd_conv_set_pointwise_tma(int enable) { g_pw = enable; }
+// bit 0: stride-1 3x3x3 / 1x3x3 weight gradients with channel counts in multiples of 64 take the TMA-fed kernel of conv_wgrad_tma.cu
+// instead of the cp.async one (conv_wgrad_tc.cu); bit 1: descriptors carry base_offset = (start >> 7) & 7 for row-shifted starts;
+// bit 2: one N = 64 MMA per dx tap instead of the N = 192 stack (A/B of the descriptor model).
+void nnd_conv_set_wgrad_tma(int mode) { g_wgrad_tma = mode; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -157,7 +167,7 @@ int nnd_conv_trace_dump(const char* path) {
 
 // Dry-run dispatch queries (host only, no CUDA call -- usable without a GPU): which kernel would serve this launch under the current
 // switches.  gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2; wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
-// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2.  Negative: bad geometry.
+// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2, 6 conv_wgrad_tma.  Negative: bad geometry.
 int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
                              int has_bias, int has_residual, int has_stats) {
   ConvGeom g;
@@ -181,6 +191,7 @@ int nnd_conv_wgrad_dispatch(const int* geom, int Cdy, int Cx) {
   if (g_force_igemm) return 0;
   if (g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) return 3;
   if (g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) return 4;
+  if (g_wgrad_tc && (g_wgrad_tma & 1) && nnd_conv_wgrad_tma_supported(g, Cdy, Cx)) return 6;
   if (g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) return 2;
   if (g_wgrad_tc && g_wgrad_strided && nnd_conv_wgrad_tc_strided_supported(g, Cdy, Cx)) return 5;
   return nnd_conv_wgrad_halo_supported(g, Cdy, Cx) ? 1 : 0;
@@ -247,8 +258,26 @@ int nnd_conv_upconv_bf16(const void* x, const void* w_packed, int N, int D, int 
   return nnd_conv_upconv(x, w_packed, N, D, H, W, Cin, Cout, sd, sh, sw, out, bias, residual, st);
 }
 
+// Workspace the weight-gradient launch can use (split-K partials of the TMA-fed kernel: plain stores + one finishing pass instead of
+// splits x as many atomics into dW); 0 when the dispatch takes a kernel that needs none.  Host only, no CUDA call.
+long long nnd_conv_wgrad_workspace_bytes(const int* geom, int Cdy, int Cx, int Cout, int Cin) {
+  ConvGeom g;
+  if (parse_geom(geom, g) != NND_OK) return 0;
+  if (nnd_conv_wgrad_dispatch(geom, Cdy, Cx) != 6) return 0;
+  return nnd_conv_wgrad_tma_workspace(g, Cdy, Cx, Cout, Cin);
+}
+
+int nnd_conv_wgrad_bf16_ws(const void* dy, int Cdy, const void* x, int Cx, const int* geom, float* dw, long long s_co,
+                           long long s_ci, long long s_tap, int Cout, int Cin, void* ws, long long ws_bytes, cudaStream_t st);
+
 int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const int* geom, float* dw, long long s_co,
                         long long s_ci, long long s_tap, int Cout, int Cin, cudaStream_t st) {
+  return nnd_conv_wgrad_bf16_ws(dy, Cdy, x, Cx, geom, dw, s_co, s_ci, s_tap, Cout, Cin, nullptr, 0, st);
+}
+
+// Same launch with an optional caller-provided workspace of nnd_conv_wgrad_workspace_bytes (smaller / null: the atomics path).
+int nnd_conv_wgrad_bf16_ws(const void* dy, int Cdy, const void* x, int Cx, const int* geom, float* dw, long long s_co,
+                           long long s_ci, long long s_tap, int Cout, int Cin, void* ws, long long ws_bytes, cudaStream_t st) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) {
@@ -258,6 +287,15 @@ int nnd_conv_wgrad_bf16(const void* dy, int Cdy, const void* x, int Cx, const in
   // g_wgrad_tc: 1 = tcgen05 wgrad kernels (default), 2 = also the stacked 32-channel one on small volumes (tests), 4 = the
   // all-taps 128-output-channel kernel of conv_wgrad_tcn.cu (opt-in: measured SLOWER than the filter-row kernel, 0.38 vs
   // 0.23 ms at 32^3 x 4 -- its N = 48 MMAs cost 44 cycles for 24 cycles of math; kept as the A/B record of that experiment)
+  if (!g_force_igemm && g_wgrad_tc && g_wgrad_tc != 4 && (g_wgrad_tma & 1) && nnd_conv_wgrad_tma_supported(g, Cdy, Cx)) {
+    int r;
+    {
+      TraceScope ts("wgrad", "wgrad_tma", g, Cx, Cdy, st);
+      r = nnd_conv_wgrad_tma((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, g_wgrad_tma,
+                             (g_wgrad_tma & 64) ? nullptr : ws, ws_bytes, st);
+    }
+    if (r != NND_ERR_ARG) return r;          // NND_ERR_ARG: no tensor map for this shape -> the cp.async kernels below
+  }
   const char* wk = "wgrad_generic";
   if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) wk = "wgrad_tcn";
   else if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) wk = "wgrad_tc";

@@ -289,9 +289,10 @@ def test_dispatch_table_of_the_luna_train_step():
     by = {r[0]: r for r in rows}
     assert abs(sum(totals.values()) - 8242) < 15 and 0.89 < frac < 0.92
     assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")
-    assert by["encoder.stage2.conv2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tc")
+    assert by["encoder.stage2.conv2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tma (TMA)")    # 128 -> 128: TMA-fed wgrad (default since round 2)
+    assert by["encoder.stage1.conv2"][7] == "conv_wgrad_tma (TMA)" and by["head.regressor.c_in@P3"][7] == "conv_wgrad_tma (TMA)"
     assert by["encoder.stage1.conv1"][5] == "conv_igemm (mma.sync)" and by["encoder.stage1.conv1"][7] == "wgrad halo (mma.sync)"
-    assert by["head.regressor.conv_out@P2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tc")
+    assert by["head.regressor.conv_out@P2"][5:8] == ("conv_tc", "conv_tc", "conv_wgrad_tma (TMA)")   # dy padded to 192 channels: 3 x 64
     rows, totals, frac_x = dr.report("luna", experimental=True, quiet=True)
     by = {r[0]: r for r in rows}
     assert 0.96 < frac_x < 0.985

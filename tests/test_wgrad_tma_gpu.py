@@ -1,0 +1,90 @@
+"""TMA-fed tcgen05 weight gradient (csrc/conv_wgrad_tma.cu: 5-D tensor-map boxes out of the NDHWC tensors, MN-major SWIZZLE_128B operands,
+the three dx taps stacked along N through row-shifted descriptor starts) against the fp32 CPU oracle of the same bf16-exact operands
+(torch.nn.grad.conv3d_weight == the autograd of nndet/arch/conv.py:344-348) and against the cp.async kernel it replaces
+(conv_wgrad_tc.cu; only the accumulation order differs).  Shapes cover both unit forms (16 w x 4 h / 8 w x 8 h), ragged widths and
+heights, one- and two-block co tiles, partial co tiles, several ci tiles, the 4^3 level and a 1x3x3 filter."""
+import csv
+import os
+import tempfile
+
+import pytest
+import torch
+
+import tutil as util  # noqa: F401
+from test_net_gpu import q, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # cin, cout, (D, H, W), batch, kernel
+    (64, 64, (4, 8, 16), 1, 3),
+    (128, 128, (5, 6, 32), 2, 3),
+    (64, 128, (3, 9, 20), 1, 3),          # wide units, second segment 4 wide, H = 9
+    (128, 64, (4, 8, 8), 2, 3),           # narrow units
+    (128, 128, (6, 7, 24), 1, 3),         # narrow, three segments per row, odd H
+    (256, 320, (4, 4, 8), 1, 3),          # three co tiles (the last one half empty), two ci tiles
+    (320, 128, (4, 4, 4), 2, 3),          # five one-block ci tiles, 4^3 level (boxes larger than the tensor)
+    (64, 64, (5, 12, 12), 1, (1, 3, 3)),  # 1x3x3 filter: three filter rows
+    (128, 192, (2, 5, 40), 1, 3),         # narrow (40 < 48), co tile 2 with one real block
+]
+
+
+def _wgrad(ops, layer, x, dy, cin, cout, sp, bs):
+    plan = layer.plan(bs, tuple(sp))
+    T = plan.T
+    dw = torch.zeros(tuple(layer.conv.weight.shape), dtype=torch.float32, device=x.device)
+    ops.trace_start()
+    for g in plan.wgrad:
+        ops.conv_wgrad(dy, cout, x, cin, g, dw, cin * T, T, 1, cout, cin)
+    with tempfile.TemporaryDirectory() as td:
+        ops.trace_dump(os.path.join(td, "t.csv"))
+        kernels = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
+    return dw.cpu(), kernels
+
+
+@pytest.mark.parametrize("cin,cout,sp,bs,k", CASES)
+def test_wgrad_tma_vs_oracle_and_cp_async_kernel(cin, cout, sp, bs, k):
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.arch.conv import ConvInstanceRelu
+    pad = 1 if isinstance(k, int) else tuple(v // 2 for v in k)
+    layer = ConvInstanceRelu(3, cin, cout, kernel_size=k, stride=1, padding=pad).cuda()
+    g = torch.Generator().manual_seed(71 + cin + cout + sp[2])
+    x = q(torch.randn(bs, cin, *sp, generator=g))
+    dy = q(torch.randn(bs, cout, *sp, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, tuple(layer.conv.weight.shape), dy, stride=1, padding=pad)     # fp32 on the CPU
+    xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    dym = dy.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    res = {}
+    try:
+        for mode in (1, 65, 0):     # split-K partials in a workspace + finishing pass (default) | atomics straight into dW | cp.async kernel
+            ops.set_wgrad_tma(mode)
+            res[mode] = _wgrad(ops, layer, xm, dym, cin, cout, sp, bs)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+    assert res[1][1] == ["wgrad_tma"] and res[65][1] == ["wgrad_tma"] and "wgrad_tma" not in res[0][1]
+    assert rel_err(res[65][0], ref) < 1e-4
+    assert rel_err(res[1][0], ref) < 1e-4            # fp32 accumulation of exact bf16 products: only the summation order differs
+    assert rel_err(res[1][0], res[0][0]) < 1e-4
+
+
+def test_descriptor_model_base_offset_must_stay_zero():
+    """The finding the kernel rests on (first B200 run of scripts/probe_wgrad_tma.py): a SWIZZLE_128B operand may start at ANY 128-byte row
+    of a TMA-written box with base_offset = 0 -- the swizzle is a function of the absolute shared-memory address -- while filling
+    base_offset with (start >> 7) & 7 shifts the pattern a second time and yields garbage."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.arch.conv import ConvInstanceRelu
+    layer = ConvInstanceRelu(3, 64, 64, kernel_size=3, stride=1, padding=1).cuda()
+    g = torch.Generator().manual_seed(5)
+    sp, bs = (4, 8, 16), 1
+    x = q(torch.randn(bs, 64, *sp, generator=g))
+    dy = q(torch.randn(bs, 64, *sp, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, tuple(layer.conv.weight.shape), dy, stride=1, padding=1)
+    xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    dym = dy.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    err = {}
+    try:
+        for mode in (1, 5, 3):          # stacked N = 192 | one N = 64 MMA per tap | stacked with base_offset
+            ops.set_wgrad_tma(mode)
+            err[mode] = rel_err(_wgrad(ops, layer, xm, dym, 64, 64, sp, bs)[0], ref)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+    assert err[1] < 1e-4 and err[5] < 1e-4 and err[3] > 0.5
