@@ -131,7 +131,7 @@ void nnd_conv_set_tcs_map(int mode);                  /* A/B switch: halo copy l
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */
 /* Profiling aid (off by default): one row per convolution-family launch -- kind (fprop | wgrad | first_*), the kernel the dispatch
  * chose, the geometry, and the launch's duration from two CUDA events on its stream.  trace(1) clears + starts, trace(0) stops;
- * trace_dump synchronises the device and writes CSV (idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop). */
+ * trace_dump synchronises the device and writes CSV (idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop,t0_ms,stream: t0_ms = start relative to the first traced launch, i.e. a per-stream timeline). */
 void nnd_conv_trace(int enable);
 long long nnd_conv_trace_count(void);
 int nnd_conv_trace_dump(const char* path);

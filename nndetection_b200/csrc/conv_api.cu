@@ -81,6 +81,7 @@ struct TraceRec {
   const char* kernel;    // dispatch decision
   int N, Di, Hi, Wi, Cin, Cout, Ld, Lh, Lw, sd, sh, sw, T;
   cudaEvent_t e0, e1;
+  cudaStream_t st;
 };
 int g_trace_on = 0;
 std::vector<TraceRec> g_trace;
@@ -91,7 +92,7 @@ struct TraceScope {
   cudaStream_t st;
   TraceScope(const char* kind, const char* kernel, const ConvGeom& g, int Cin, int Cout, cudaStream_t s) : st(s) {
     if (!g_trace_on) return;
-    TraceRec r{kind, kernel, g.N, g.Di, g.Hi, g.Wi, Cin, Cout, g.Ld, g.Lh, g.Lw, g.sd, g.sh, g.sw, g.T, nullptr, nullptr};
+    TraceRec r{kind, kernel, g.N, g.Di, g.Hi, g.Wi, Cin, Cout, g.Ld, g.Lh, g.Lw, g.sd, g.sh, g.sw, g.T, nullptr, nullptr, s};
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
     cudaEventRecord(r.e0, st);
     std::lock_guard<std::mutex> lk(g_trace_mu);
@@ -152,14 +153,16 @@ int nnd_conv_trace_dump(const char* path) {
   std::lock_guard<std::mutex> lk(g_trace_mu);
   FILE* f = fopen(path, "w");
   if (!f) return NND_ERR_ARG;
-  fprintf(f, "idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop\n");
+  fprintf(f, "idx,kind,kernel,N,Di,Hi,Wi,Cin,Cout,Ld,Lh,Lw,sd,sh,sw,T,ms,gflop,t0_ms,stream\n");
   for (size_t i = 0; i < g_trace.size(); ++i) {
     const TraceRec& r = g_trace[i];
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { ms = -1.f; (void)cudaGetLastError(); }
     const double gf = 2.0 * r.N * (double)r.Ld * r.Lh * r.Lw * r.T * r.Cin * r.Cout * 1e-9;
-    fprintf(f, "%zu,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.4f\n", i, r.kind, r.kernel, r.N, r.Di, r.Hi, r.Wi, r.Cin,
-            r.Cout, r.Ld, r.Lh, r.Lw, r.sd, r.sh, r.sw, r.T, ms, gf);
+    float t0 = -1.f;                                  // start of the launch relative to the first traced launch: a per-stream timeline
+    if (cudaEventElapsedTime(&t0, g_trace[0].e0, r.e0) != cudaSuccess) { t0 = -1.f; (void)cudaGetLastError(); }
+    fprintf(f, "%zu,%s,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.4f,%.6f,%llx\n", i, r.kind, r.kernel, r.N, r.Di, r.Hi, r.Wi, r.Cin,
+            r.Cout, r.Ld, r.Lh, r.Lw, r.sd, r.sh, r.sw, r.T, ms, gf, t0, (unsigned long long)(size_t)r.st);
   }
   fclose(f);
   return NND_OK;

@@ -29,7 +29,8 @@
 
 namespace {
 
-constexpr int WM_THREADS = 6 * 32;
+constexpr int WM_NI = 2;                      // MMA issuer warps (alternate pipeline stages)
+constexpr int WM_THREADS = (1 + WM_NI + 4) * 32;
 constexpr int WM_KSTEPS = 4;                   // 16-voxel K-steps per stage (64 voxels)
 constexpr int WM_ABLK = 64 * 128;              // one 64-channel block of dy: 64 K rows x 128 B
 constexpr int WM_SMEM_MAX = 232448 - 2048;     // dynamic shared memory minus alignment slack
@@ -52,6 +53,8 @@ struct WmArgs {
   int n_groups;
   signed char gdz[9], gdy[9];
   unsigned char gtw[9][3];          // weight tap index of dx = -1, 0, +1
+  unsigned char gtw2[9][3];         // pair mode: taps of filter row (dz, dy - 1) accumulated in MMA rows 64..127 (255 = row absent)
+  int pair;                         // Cdy == 64: the second 64-row half of the MMA takes dy shifted by one h row = the filter row above
   int ci_tiles;
   int mode;                         // bit 1: base_offset = (start >> 7) & 7, bit 2: one N = 64 MMA per tap instead of the N = 192 stack
                                     // timing experiments (wrong results): bit 3 no epilogue atomics, bit 4 no MMAs, bit 5 no TMA loads
@@ -119,14 +122,20 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
   const int n_units = u1 > u0 ? (int)(u1 - u0) : 0;
   const int dz = a.gdz[grp], ty = a.gdy[grp];
   const int a_blocks = (a.Cdy - co0) >= 128 ? 2 : 1;          // 64-channel blocks of dy this co tile really has
+  // Pair mode (64 output channels): ONE dy box with an extra h row; MMA rows 64..127 read it one h row further (LBO = one row of the
+  // box), i.e. D[64 + co][dx, ci] = sum dy[h + 1][co] * x[h + ty][ci] = the filter row (dz, ty - 1).  Units start at h = -1 so that
+  // dy row 0 meets x row ty - 1 as well.  Six CTA groups instead of nine for a 3x3x3 filter, every MMA row but one group's half used.
+  const int pair = a.pair;
+  constexpr int BH_ = NARROW ? 8 : 4, BW_ = NARROW ? 8 : 16;
+  const unsigned lbo_a = pair ? (unsigned)(BW_ * 128) : (unsigned)WM_ABLK;
 
   // a co tile with one real block: rows 64..127 of every stage stay zero for the whole kernel (zero MMA rows)
-  if (a_blocks == 1)
+  if (a_blocks == 1 && !pair)
     for (int i = tid; i < STAGES * (WM_ABLK / 16); i += WM_THREADS)
       reinterpret_cast<uint4*>(smem + (size_t)(i / (WM_ABLK / 16)) * STAGE_BYTES + WM_ABLK)[i % (WM_ABLK / 16)] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(FULL(i), 1); mbar_init(EMPTY(i), 1); }
-    mbar_init(DONE, 1);
+    mbar_init(DONE, WM_NI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -138,7 +147,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = s_tmem_base;
-  if (warp >= 2) {                                 // accumulators start at zero: every MMA accumulates, an idle CTA adds zeros
+  if (warp >= 1 + WM_NI) {                         // accumulators start at zero: every MMA accumulates, an idle CTA adds zeros
     const int q = warp & 3;
     for (int c = 0; c < NB * 192; c += 32) tmem_zero32(tmem_base + ((unsigned)(q * 32) << 16) + c);
   }
@@ -150,12 +159,12 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     // ================================================================ TMA producer
     if (lane == 0) {
       unsigned stage = 0, phase = 0;
-      const unsigned tx = (unsigned)(a_blocks * WM_ABLK + NB * BBLK);
+      const unsigned tx = (unsigned)((pair ? (BH_ + 1) * BW_ * 128 : a_blocks * WM_ABLK) + NB * BBLK);
       WmCursor it;
       it.init(u0, a);
       for (int i = 0; i < n_units; ++i, it.next(a)) {
         if ((unsigned)(it.d + dz) >= (unsigned)a.D) continue;            // the whole x box is padding: nothing to add
-        const int w0 = it.ws * (NARROW ? 8 : 16), h0 = it.hb * (NARROW ? 8 : 4);
+        const int w0 = it.ws * BW_, h0 = it.hb * BH_ - pair;
         mbar_wait(EMPTY(stage), phase ^ 1);
         const unsigned sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
         if (a.mode & 32) { mbar_arrive(FULL(stage)); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
@@ -168,39 +177,61 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer (the whole warp runs the control flow, the elected
-    // lane issues: scripts/mma_rate.cu -- a divergent single-lane loop costs 81 instead of 48 issue cycles per MMA)
-    unsigned stage = 0, phase = 0;
+  } else if (warp <= WM_NI) {
+    // ================================================================ MMA issuers (the whole warp runs the control flow, the elected
+    // lane issues: scripts/mma_rate.cu -- a divergent single-lane loop costs 81 instead of 48 issue cycles per MMA).  Two warps take
+    // alternate stages: with one, ~370 cycles of per-stage bookkeeping (barrier poll, fence, descriptor set-up, commit) were exposed
+    // between the 8 x ~105-cycle MMAs of a stage (second device run: 1260 cycles per stage without any TMA traffic).  Every MMA
+    // accumulates onto zero-initialised TMEM, so the order between the two issue streams does not matter.
+    const int me = warp - 1;
+    unsigned stage = 0, phase = 0, turn = 0;
     const unsigned tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const int use_bo = (a.mode >> 1) & 1, unstacked = (a.mode >> 2) & 1;
+    const int use_bo = (a.mode >> 1) & 1, unstacked = (a.mode >> 2) & 1, slow = (a.mode & 6) != 0, no_mma = (a.mode & 16) != 0;
+    // loop-invariant descriptor halves (base_offset 0): only the 14-bit start field moves
+    const unsigned a_hi = wm_hi(0, 1024, 0), b_hi = wm_hi(0, SBO_B, 0);
+    const unsigned smem0 = smem_u32(smem);
     WmCursor it;
     it.init(u0, a);
     for (int i = 0; i < n_units; ++i, it.next(a)) {
       if ((unsigned)(it.d + dz) >= (unsigned)a.D) continue;
-      mbar_wait_warp(FULL(stage), phase, lane);
-      tc_fence_after();
-      if (elect_one()) {
-        const unsigned sa = smem_u32(smem + (size_t)stage * STAGE_BYTES), sb = sa + 2 * WM_ABLK;
+      if ((int)turn == me) {
+        mbar_wait_warp(FULL(stage), phase, lane);
+        tc_fence_after();
+        if (elect_one()) {
+          const unsigned sa = smem0 + stage * STAGE_BYTES, sb = sa + 2 * WM_ABLK;
+          if (!slow) {
+            const unsigned a_lo0 = wm_lo(sa, lbo_a), b_lo0 = wm_lo(sb, 128);
+            if (!no_mma) {
 #pragma unroll
-        for (int j = 0; j < ((a.mode & 16) ? 0 : WM_KSTEPS); ++j) {
-          const unsigned astart = sa + j * 2048;                          // 16 K rows of dy; co block 1 one box further
-          const unsigned a_lo = wm_lo(astart, WM_ABLK), a_hi = wm_hi(astart, 1024, use_bo);
+              for (int j = 0; j < WM_KSTEPS; ++j)
 #pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const unsigned bstart = sb + b * BBLK + j * RSTEP * 128;      // tap dx = -1; dx = 0, +1 one / two rows further
-            if (!unstacked) {
-              tc_mma2(tm + b * 192, a_lo, a_hi, wm_lo(bstart, 128), wm_hi(bstart, SBO_B, use_bo), IDESC192, 1u);
-            } else {
-#pragma unroll
-              for (int t = 0; t < 3; ++t)
-                tc_mma2(tm + b * 192 + t * 64, a_lo, a_hi, wm_lo(bstart + t * 128, 128), wm_hi(bstart + t * 128, SBO_B, use_bo), IDESC64, 1u);
+                for (int b = 0; b < NB; ++b)
+                  tc_mma_acc2(tm + b * 192, a_lo0 + ((j * 2048) >> 4), a_hi, b_lo0 + ((b * BBLK + j * RSTEP * 128) >> 4), b_hi, IDESC192);
+            }
+          } else {
+            // A/B variants of the descriptor model (tests/test_wgrad_tma_gpu.py): base_offset = (start >> 7) & 7 and / or one N = 64
+            // MMA per dx tap instead of the N = 192 stack
+#pragma unroll 1
+            for (int j = 0; j < WM_KSTEPS; ++j) {
+              const unsigned astart = sa + j * 2048;
+#pragma unroll 1
+              for (int b = 0; b < NB; ++b) {
+                const unsigned bstart = sb + b * BBLK + j * RSTEP * 128;
+                if (!unstacked) {
+                  tc_mma2(tm + b * 192, wm_lo(astart, lbo_a), wm_hi(astart, 1024, use_bo), wm_lo(bstart, 128), wm_hi(bstart, SBO_B, use_bo), IDESC192, 1u);
+                } else {
+                  for (int t = 0; t < 3; ++t)
+                    tc_mma2(tm + b * 192 + t * 64, wm_lo(astart, lbo_a), wm_hi(astart, 1024, use_bo), wm_lo(bstart + t * 128, 128),
+                            wm_hi(bstart + t * 128, SBO_B, use_bo), IDESC64, 1u);
+                }
+              }
             }
           }
+          tc_commit(EMPTY(stage));
         }
-        tc_commit(EMPTY(stage));
+        __syncwarp();
       }
-      __syncwarp();
+      turn = (turn + 1 == WM_NI) ? 0 : turn + 1;
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     if (elect_one()) tc_commit(DONE);
@@ -211,14 +242,16 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     // CTA, idle ones store zeros), wgrad_finish_kernel sums the splits.  Without: fp32 atomics straight into dW (first device run: 42 of
     // the 155 us of a 128 -> 128 @32^3 launch -- 49 152 REDG lane-operations per CTA at ~1.3 cycles each, 7 M atomics per launch).
     const int q = warp & 3;
-    const int co = co0 + q * 32 + lane;
+    const int upper = pair && q >= 2;               // pair mode: TMEM lanes 64..127 hold the filter row above for co = lane - 64
+    const int co = co0 + (pair ? (q & 1) : q) * 32 + lane;
     mbar_wait_warp_backoff(DONE, 0, lane, 1000);   // the wait lasts the whole kernel
     tc_fence_after();
 #pragma unroll 1
     for (int b = 0; b < NB; ++b) {
 #pragma unroll 1
       for (int t = 0; t < 3; ++t) {
-        const int tw = a.gtw[grp][t];
+        const int tw = upper ? a.gtw2[grp][t] : a.gtw[grp][t];
+        if (tw == 255) continue;                       // pair mode: the filter has no row above this group's
         float* dwt = a.dw + (long long)tw * a.s_tap + (long long)co * a.s_co;
         float* pt = a.part ? a.part + (((long long)blockIdx.x * a.T + tw) * a.Cout + co) * a.Cin : nullptr;
 #pragma unroll 1
@@ -308,9 +341,7 @@ long long wm_plan_splits(long long total_units, long long tiles, long long* unit
 }
 
 template <int NB, int NARROW>
-int launch_wm(const CUtensorMap& map_dy, const CUtensorMap& map_x, WmArgs a, int co_tiles, void* ws, long long ws_bytes, cudaStream_t st) {
-  const long long tiles = (long long)a.n_groups * co_tiles * a.ci_tiles;
-  const long long splits = wm_plan_splits(a.total_units, tiles, &a.units_per_split);
+int launch_wm(const CUtensorMap& map_dy, const CUtensorMap& map_x, WmArgs a, long long splits, void* ws, long long ws_bytes, cudaStream_t st) {
   const long long block = (long long)a.T * a.Cout * a.Cin;          // floats per split
   a.part = (ws && ws_bytes >= splits * block * 4 && !((size_t)ws & 15)) ? reinterpret_cast<float*>(ws) : nullptr;
   constexpr size_t SMEM = (size_t)wm_stages(NB, NARROW) * wm_stage_bytes(NB, NARROW) + 1024;
@@ -318,7 +349,7 @@ int launch_wm(const CUtensorMap& map_dy, const CUtensorMap& map_x, WmArgs a, int
   if (attr_set.need()) {
     NND_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<NB, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
   }
-  dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(co_tiles * a.ci_tiles));
+  dim3 grid((unsigned)splits, (unsigned)a.n_groups, (unsigned)(((a.Cdy + 127) / 128) * a.ci_tiles));
   conv_wgrad_tma_kernel<NB, NARROW><<<grid, WM_THREADS, SMEM, st>>>(map_dy, map_x, a);
   NND_LAUNCH_CHECK("conv_wgrad_tma_kernel");
   if (a.part) {
@@ -350,68 +381,79 @@ int nnd_conv_wgrad_tma_supported(const ConvGeom& g, int Cdy, int Cx) {
 }
 
 namespace {
-// narrow units (8 w x 8 h) when they pad the width less than 16-voxel row segments do
-int wm_narrow(int W) { return ((W + 7) / 8) * 8 < ((W + 15) / 16) * 16 ? 1 : 0; }
-int wm_groups(const ConvGeom& g) {
-  int rows[3][3] = {}, n = 0;
-  for (int t = 0; t < g.T; ++t) rows[g.off_d[t] + 1][g.off_h[t] + 1] = 1;
-  for (int z = 0; z < 3; ++z) for (int y = 0; y < 3; ++y) n += rows[z][y];
-  return n;
+// Launch plan shared by the launcher and the workspace query.
+struct WmPlan {
+  int narrow, bw, bh, pair, nb, co_tiles;
+  WmArgs a;                       // geometry part filled in (units, groups, ci_tiles, units_per_split)
+  long long splits;
+};
+
+void wm_plan(const ConvGeom& g, int Cdy, int Cx, WmPlan& p) {
+  const int W = g.Lw, H = g.Lh, D = g.Ld;
+  // narrow units (8 w x 8 h) when they pad the width less than 16-voxel row segments do
+  p.narrow = ((W + 7) / 8) * 8 < ((W + 15) / 16) * 16 ? 1 : 0;
+  p.bw = p.narrow ? 8 : 16; p.bh = p.narrow ? 8 : 4;
+  p.pair = Cdy == 64 ? 1 : 0;
+  WmArgs& a = p.a;
+  a.pair = p.pair;
+  a.D = D; a.H = H; a.W = W;
+  a.HB = (H + p.pair + p.bh - 1) / p.bh;                 // pair mode: units cover h = -1 .. H - 1
+  a.WS = (W + p.bw - 1) / p.bw;
+  a.total_units = (long long)g.N * D * a.HB * a.WS;
+  // CTA groups: one per (dz, dy) filter row; pair mode: one per two rows (dy, dy - 1), walking down from dy = +1
+  unsigned char rows[3][3][3];
+  int present[3][3] = {};
+  for (int t = 0; t < g.T; ++t) {
+    rows[g.off_d[t] + 1][g.off_h[t] + 1][g.off_w[t] + 1] = g.tap_w[t];
+    present[g.off_d[t] + 1][g.off_h[t] + 1] = 1;
+  }
+  a.n_groups = 0;
+  for (int z = 0; z < 3; ++z)
+    for (int y = 2; y >= 0; --y) {
+      if (!present[z][y]) continue;
+      const int n = a.n_groups++;
+      a.gdz[n] = (signed char)(z - 1); a.gdy[n] = (signed char)(y - 1);
+      for (int k = 0; k < 3; ++k) { a.gtw[n][k] = rows[z][y][k]; a.gtw2[n][k] = 255; }
+      if (p.pair && y > 0 && present[z][y - 1]) {
+        for (int k = 0; k < 3; ++k) a.gtw2[n][k] = rows[z][y - 1][k];
+        --y;                                              // the row below is served by this group's upper half
+      }
+    }
+  p.co_tiles = (Cdy + 127) / 128;
+  p.nb = Cx % 128 == 0 ? 2 : 1;
+  a.ci_tiles = Cx / (64 * p.nb);
+  const long long tiles = (long long)a.n_groups * p.co_tiles * a.ci_tiles;
+  p.splits = a.total_units > 0 ? wm_plan_splits(a.total_units, tiles, &a.units_per_split) : 0;
 }
 }  // namespace
 
 // Bytes of split-K partials nnd_conv_wgrad_tma wants as its workspace for this launch (0: none needed).  Host only.
 long long nnd_conv_wgrad_tma_workspace(const ConvGeom& g, int Cdy, int Cx, int Cout, int Cin) {
-  const int narrow = wm_narrow(g.Lw);
-  const int bw = narrow ? 8 : 16, bh = narrow ? 8 : 4;
-  const long long units = (long long)g.N * g.Ld * ((g.Lh + bh - 1) / bh) * ((g.Lw + bw - 1) / bw);
-  if (units <= 0) return 0;
-  const int nb = Cx % 128 == 0 ? 2 : 1;
-  const long long tiles = (long long)wm_groups(g) * ((Cdy + 127) / 128) * (Cx / (64 * nb));
-  long long ups;
-  const long long splits = wm_plan_splits(units, tiles, &ups);
-  return splits * g.T * (long long)Cout * Cin * 4;
+  WmPlan p;
+  wm_plan(g, Cdy, Cx, p);
+  return p.splits * g.T * (long long)Cout * Cin * 4;
 }
 
 int nnd_conv_wgrad_tma(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                        long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
                        cudaStream_t st) {
   if (((size_t)dy & 15) || ((size_t)x & 15)) return NND_ERR_ARG;
-  const int W = g.Lw, H = g.Lh, D = g.Ld;
-  const int narrow = wm_narrow(W);
-  const int bw = narrow ? 8 : 16, bh = narrow ? 8 : 4;
-  WmArgs a;
-  a.T = g.T; a.part = nullptr;
+  WmPlan p;
+  wm_plan(g, Cdy, Cx, p);
+  WmArgs& a = p.a;
+  if (a.total_units <= 0) return NND_OK;
+  a.dw = dw; a.s_co = s_co; a.s_ci = s_ci; a.s_tap = s_tap; a.Cout = Cout; a.Cin = Cin; a.Cdy = Cdy;
+  a.T = g.T; a.part = nullptr; a.mode = mode;
   {
     // the partials are indexed by weight tap: usable when the taps are exactly the slices 0 .. T-1 and whole 32-channel chunks are real
     unsigned seen = 0;
     for (int t = 0; t < g.T; ++t) if (g.tap_w[t] < 32) seen |= 1u << g.tap_w[t];
     if (seen != (g.T >= 32 ? 0xffffffffu : (1u << g.T) - 1u) || Cin % 32) { ws = nullptr; ws_bytes = 0; }
   }
-  a.dw = dw; a.s_co = s_co; a.s_ci = s_ci; a.s_tap = s_tap; a.Cout = Cout; a.Cin = Cin; a.Cdy = Cdy;
-  a.D = D; a.H = H; a.W = W; a.HB = (H + bh - 1) / bh; a.WS = (W + bw - 1) / bw;
-  a.total_units = (long long)g.N * D * a.HB * a.WS;
-  if (a.total_units <= 0) return NND_OK;
-  a.mode = mode;
-  a.n_groups = 0;
-  for (int z = -1; z <= 1; ++z)
-    for (int y = -1; y <= 1; ++y) {
-      int found = 0;
-      unsigned char tw[3] = {255, 255, 255};
-      for (int t = 0; t < g.T; ++t)
-        if (g.off_d[t] == z && g.off_h[t] == y) { tw[g.off_w[t] + 1] = g.tap_w[t]; found = 1; }
-      if (found) {
-        a.gdz[a.n_groups] = (signed char)z; a.gdy[a.n_groups] = (signed char)y;
-        for (int k = 0; k < 3; ++k) a.gtw[a.n_groups][k] = tw[k];
-        ++a.n_groups;
-      }
-    }
   CUtensorMap map_dy, map_x;
-  if (wm_make_map(&map_dy, dy, g.N, D, H, W, Cdy, bw, bh) != NND_OK || wm_make_map(&map_x, x, g.N, D, H, W, Cx, bw + 2, bh) != NND_OK)
+  if (wm_make_map(&map_dy, dy, g.N, a.D, a.H, a.W, Cdy, p.bw, p.bh + p.pair) != NND_OK ||
+      wm_make_map(&map_x, x, g.N, a.D, a.H, a.W, Cx, p.bw + 2, p.bh) != NND_OK)
     return NND_ERR_ARG;                                                    // the caller falls back to the cp.async kernel
-  const int co_tiles = (Cdy + 127) / 128;
-  const int nb = Cx % 128 == 0 ? 2 : 1;
-  a.ci_tiles = Cx / (64 * nb);
-  if (nb == 2) return narrow ? launch_wm<2, 1>(map_dy, map_x, a, co_tiles, ws, ws_bytes, st) : launch_wm<2, 0>(map_dy, map_x, a, co_tiles, ws, ws_bytes, st);
-  return narrow ? launch_wm<1, 1>(map_dy, map_x, a, co_tiles, ws, ws_bytes, st) : launch_wm<1, 0>(map_dy, map_x, a, co_tiles, ws, ws_bytes, st);
+  if (p.nb == 2) return p.narrow ? launch_wm<2, 1>(map_dy, map_x, a, p.splits, ws, ws_bytes, st) : launch_wm<2, 0>(map_dy, map_x, a, p.splits, ws, ws_bytes, st);
+  return p.narrow ? launch_wm<1, 1>(map_dy, map_x, a, p.splits, ws, ws_bytes, st) : launch_wm<1, 0>(map_dy, map_x, a, p.splits, ws, ws_bytes, st);
 }

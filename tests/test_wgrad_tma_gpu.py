@@ -25,6 +25,8 @@ CASES = [  # cin, cout, (D, H, W), batch, kernel
     (320, 128, (4, 4, 4), 2, 3),          # five one-block ci tiles, 4^3 level (boxes larger than the tensor)
     (64, 64, (5, 12, 12), 1, (1, 3, 3)),  # 1x3x3 filter: three filter rows
     (128, 192, (2, 5, 40), 1, 3),         # narrow (40 < 48), co tile 2 with one real block
+    (192, 64, (3, 7, 20), 2, 3),          # 64 output channels: paired filter rows, odd H (the h = -1 row), three one-block ci tiles
+    (64, 64, (2, 8, 8), 2, (1, 3, 3)),    # paired rows, narrow units, 1x3x3
 ]
 
 
