@@ -204,6 +204,9 @@ def main():
         conv_ops.set_pointwise_tma(True)
     if "no_pw_tma" in args.experimental.split(","):
         conv_ops.set_pointwise_tma(False)
+    for tok in args.experimental.split(","):                  # gather_tma=<mode>: TMA-fed tile kernel (bit 0 stride-1 forms, bit 1 stride-2 forms)
+        if tok.startswith("gather_tma="):
+            conv_ops.set_gather_tma(int(tok.split("=")[1]))
     if "no_wgrad_tma" in args.experimental.split(","):        # A/B: >= 64-channel stride-1 weight gradients back on the cp.async kernel
         conv_ops.set_wgrad_tma(0)
     if "tcs_map" in args.experimental.split(","):            # A/B: coalesced halo copy mapping in the streaming kernel

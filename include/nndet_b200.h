@@ -126,6 +126,7 @@ void nnd_conv_set_tensor_path(int enable_tcgen05);
 void nnd_conv_set_wgrad_tc(int mode);                /* A/B switch: 0 mma.sync wgrad, 1 tcgen05 (default), 2 + stacked 32-ch kernel on small volumes, 4 + all-taps 128-co kernel */
 void nnd_conv_set_wgrad_strided_tc(int enable);       /* default 1 (validated on B200, round 2): de-interleaved tcgen05 wgrad for stride-2 / transposed convolutions; 0 = mma.sync (A/B) */
 void nnd_conv_set_wgrad_tma(int mode);                /* TMA-fed tcgen05 wgrad (csrc/conv_wgrad_tma.cu) for stride-1 3x3x3 / 1x3x3 layers with channels in multiples of 64: bit 0 on, bit 1 base_offset descriptors (WRONG results: the device-verified model is base_offset 0), bit 2 unstacked taps, bits 3-5 timing experiments, bit 6 ignore the workspace (A/B) */
+void nnd_conv_set_gather_tma(int mode);               /* TMA-fed tcgen05 tile kernel (csrc/conv_tct.cu): bit 0 the stride-1 forms of the tile kernel, bit 1 the stride-2 forms (A/B; used_tc 6 / 7) */
 void nnd_conv_set_gather_strided_tc(int enable);      /* default 1 (validated on B200, round 2): de-interleaved-halo tcgen05 kernel for stride-2 gathers; 0 = mma.sync (A/B) */
 void nnd_conv_set_tcs_map(int mode);                  /* A/B switch: halo copy lane mapping of the streaming kernel (0 row-walking threads, 1 lanes along a voxel's channel groups) */
 void nnd_conv_set_stream_path(int enable, int issuers); /* A/B switch: streaming z-window tcgen05 kernel (default on, 2 issuers) */

@@ -252,6 +252,15 @@ def set_gather_strided_tc(enable: bool):
     L.lib().nnd_conv_set_gather_strided_tc(c_int(1 if enable else 0))
 
 
+GATHER_TMA_DEFAULT = 3      # on since its validation on a B200 (round 2); the C side has the same default
+
+
+def set_gather_tma(mode: int):
+    """TMA-fed variant of the tcgen05 tile kernel (csrc/conv_tct.cu).  bit 0: stride-1 forms (128-channel layers, small volumes, the
+    >= 4-tap stride-2 dgrad classes); bit 1: stride-2 convolutions and the dgrad of up-convolutions."""
+    L.lib().nnd_conv_set_gather_tma(c_int(int(mode)))
+
+
 WGRAD_TMA_DEFAULT = 1      # on since its validation on a B200 (round 2); the C side has the same default
 
 

@@ -11,6 +11,10 @@
 int nnd_conv_igemm(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tct(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tct_supported(const ConvGeom& g, const ConvEpilogue& ep);
+int nnd_conv_tct_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
+int nnd_conv_tct_s2_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tc_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st);
 int nnd_conv_tc_s2_supported(const ConvGeom& g, const ConvEpilogue& ep);
 int nnd_conv_tc_bulk_supported(const ConvGeom& g, const ConvEpilogue& ep, const void* items, int items_n_tile, int items_T);
@@ -71,6 +75,7 @@ int g_stream = 1;
 int g_wgrad_strided = 1;      // validated on a B200 in round 2 (tests/test_strided_tcgen05_gpu.py), default since
 int g_gather_strided = 1;
 int g_tc_bulk = 0;
+int g_gather_tma = 3;         // TMA-fed tile kernel (conv_tct.cu; validated on a B200 in round 2): bit 0 stride-1 forms, bit 1 stride-2 forms
 int g_wgrad_tma = 1;          // TMA-fed tcgen05 wgrad (conv_wgrad_tma.cu; validated on a B200 in round 2): bit 0 on, bits 1-5 A/B and timing variants
 int g_pw = 1;                 // TMA-fed pointwise GEMM (conv_pw.cu) for single-tap gathers (validated on a B200 in round 2; 0 = A/B)
 
@@ -130,6 +135,9 @@ void nnd_conv_set_pointwise_tma(int enable) { g_pw = enable; }
 // instead of the cp.async one (conv_wgrad_tc.cu); bit 1: descriptors carry base_offset = (start >> 7) & 7 for row-shifted starts;
 // bit 2: one N = 64 MMA per dx tap instead of the N = 192 stack (A/B of the descriptor model).
 void nnd_conv_set_wgrad_tma(int mode) { g_wgrad_tma = mode; }
+// bit 0: launches the tcgen05 tile kernel serves (conv_tc.cu: 128-channel stride-1 layers, small volumes, >= 4-tap stride-2 dgrad classes)
+// take its TMA-fed variant (conv_tct.cu); bit 1: the same for the stride-2 forms (conv_tc.cu S2 = 1)
+void nnd_conv_set_gather_tma(int mode) { g_gather_tma = mode; }
 // 1 (default): streaming z-window tcgen05 kernel (conv_tcs.cu) for the 32/64-channel 3x3x3 stride-1 layers when the volume
 // is large enough to feed the persistent grid; 2: whenever the shape is supported (tests); 0: tile kernel.
 // issuers: 1 or 2 MMA-issuing warps in that kernel (2 = default; 1 = fixed accumulation order)
@@ -184,7 +192,9 @@ int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long 
   if (g_force_igemm) return 0;
   if (g_pw && nnd_conv_pw_supported(g, ep)) return 4;
   if (g_stream && nnd_conv_tcs_supported(g, ep) && (g_stream == 2 || nnd_conv_tcs_profitable(g, ep))) return 2;
+  if (g_gather_strided && (g_gather_tma & 2) && nnd_conv_tct_s2_supported(g, ep)) return 7;
   if (g_gather_strided && nnd_conv_tc_s2_supported(g, ep)) return 3;
+  if ((g_gather_tma & 1) && nnd_conv_tct_supported(g, ep)) return 6;
   return nnd_conv_tc_supported(g, ep) ? 1 : 0;
 }
 
@@ -234,6 +244,14 @@ int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, v
     TraceScope ts("fprop", "conv_tcs", g, g.Cin, Cout, st);
     return nnd_conv_tcs((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
   }
+  if (!g_force_igemm && g_gather_strided && (g_gather_tma & 2) && nnd_conv_tct_s2_supported(g, ep)) {
+    int r;
+    {
+      TraceScope ts("fprop", "conv_tct_s2", g, g.Cin, Cout, st);
+      r = nnd_conv_tct_s2((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+    }
+    if (r != NND_ERR_ARG) { if (used_tc) *used_tc = 7; return r; }       // NND_ERR_ARG: no tensor map / shared memory -> cp.async kernel
+  }
   if (!g_force_igemm && g_gather_strided && nnd_conv_tc_s2_supported(g, ep)) {
     if (used_tc) *used_tc = 3;
     TraceScope ts("fprop", "conv_tc_s2", g, g.Cin, Cout, st);
@@ -243,6 +261,14 @@ int nnd_conv_gather_bf16_items(const void* in, const void* w, const int* geom, v
     if (used_tc) *used_tc = 4;
     TraceScope ts("fprop", "conv_tc_bulk", g, g.Cin, Cout, st);
     return nnd_conv_tc_bulk((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st, (const __nv_bfloat16*)w_items, items_n_tile, items_T);
+  }
+  if (!g_force_igemm && (g_gather_tma & 1) && nnd_conv_tct_supported(g, ep)) {
+    int r;
+    {
+      TraceScope ts("fprop", "conv_tct", g, g.Cin, Cout, st);
+      r = nnd_conv_tct((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, g, ep, st);
+    }
+    if (r != NND_ERR_ARG) { if (used_tc) *used_tc = 6; return r; }
   }
   const bool tc = !g_force_igemm && nnd_conv_tc_supported(g, ep);
   if (used_tc) *used_tc = tc ? 1 : 0;

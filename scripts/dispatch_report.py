@@ -13,7 +13,7 @@ from ctypes import c_int, c_longlong
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2", 4: "conv_pw (TMA)"}
+GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2", 4: "conv_pw (TMA)", 6: "conv_tct (TMA)", 7: "conv_tct S2 (TMA)"}
 WGRAD = {0: "wgrad generic (mma.sync)", 1: "wgrad halo (mma.sync)", 2: "conv_wgrad_tc", 3: "conv_wgrad_tc32", 4: "conv_wgrad_tcn",
          5: "conv_wgrad_tc SW=2", 6: "conv_wgrad_tma (TMA)"}
 

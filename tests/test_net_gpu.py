@@ -270,7 +270,12 @@ def test_tcgen05_paths_match_mma_sync_paths_and_are_used():
     x = torch.randn(2, 64, 8, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
     plan = layer.plan(2, (8, 16, 16))
     y = ops.empty_cl(2, 64, plan.out_sp)
-    assert ops.conv_gather(x, layer.packed()[0], plan.fprop[0], y, 64, 64) == 1
+    assert ops.conv_gather(x, layer.packed()[0], plan.fprop[0], y, 64, 64) == 6         # 6: TMA-fed tile kernel (conv_tct.cu)
+    ops.set_gather_tma(0)
+    try:
+        assert ops.conv_gather(x, layer.packed()[0], plan.fprop[0], y, 64, 64) == 1     # 1: its cp.async predecessor (conv_tc.cu)
+    finally:
+        ops.set_gather_tma(ops.GATHER_TMA_DEFAULT)
 
 
 AB_CASES = [

@@ -116,6 +116,7 @@ def test_strided_conv_block_forward_on_tcgen05(cin, cout, shape, s):
     xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
     res = {}
     try:
+        ops.set_gather_tma(0)                    # this test covers the cp.async kernel; its TMA-fed successor: tests/test_gather_tma_gpu.py
         for mode in (True, False):
             ops.set_gather_strided_tc(mode)
             with torch.no_grad():
@@ -123,6 +124,7 @@ def test_strided_conv_block_forward_on_tcgen05(cin, cout, shape, s):
             res[mode] = (y.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop"])
     finally:
         ops.set_gather_strided_tc(True)
+        ops.set_gather_tma(ops.GATHER_TMA_DEFAULT)
     assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
     assert rel_err(res[True][0], yr) < 5e-3
     assert rel_err(res[True][0], res[False][0]) < 3e-3
@@ -141,6 +143,7 @@ def test_upconv_input_gradient_on_tcgen05(cin, cout, shape):
     yr.backward(gy)
     res = {}
     try:
+        ops.set_gather_tma(0)                    # the cp.async kernel (see above)
         for mode in (True, False):
             ops.set_gather_strided_tc(mode)
             xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
@@ -148,6 +151,7 @@ def test_upconv_input_gradient_on_tcgen05(cin, cout, shape):
             res[mode] = (xm.grad.float().cpu(), [r["kernel"] for r in rows if r["kind"] == "fprop" and int(r["T"]) == 8 and r["kernel"] != "conv_pw_up"])
     finally:
         ops.set_gather_strided_tc(True)
+        ops.set_gather_tma(ops.GATHER_TMA_DEFAULT)
     assert res[True][1] == ["conv_tc_s2"] and res[False][1] == ["conv_igemm"]
     assert rel_err(res[True][0], xr.grad) < 5e-3
     assert rel_err(res[True][0], res[False][0]) < 3e-3
