@@ -39,6 +39,11 @@ int nnd_conv_wgrad_tma(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x,
                        long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
                        cudaStream_t st);
 long long nnd_conv_wgrad_tma_workspace(const ConvGeom& g, int Cdy, int Cx, int Cout, int Cin);
+int nnd_conv_wgrad_tma_s2_supported(const ConvGeom& g, int Cdy, int Cx);
+int nnd_conv_wgrad_tma_s2(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
+                          long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
+                          cudaStream_t st);
+long long nnd_conv_wgrad_tma_s2_workspace(const ConvGeom& g, int Cdy, int Cx, int Cout, int Cin);
 int nnd_conv_wgrad_tc32_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tc32_profitable(const ConvGeom& g);
 int nnd_conv_wgrad_tc32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ConvGeom& g, float* dw, long long s_co, long long s_ci,
@@ -133,7 +138,8 @@ void nnd_conv_set_tc_bulk(int enable) { g_tc_bulk = enable; }
 void nnd_conv_set_pointwise_tma(int enable) { g_pw = enable; }
 // bit 0: stride-1 3x3x3 / 1x3x3 weight gradients with channel counts in multiples of 64 take the TMA-fed kernel of conv_wgrad_tma.cu
 // instead of the cp.async one (conv_wgrad_tc.cu); bit 1: descriptors carry base_offset = (start >> 7) & 7 for row-shifted starts;
-// bit 2: one N = 64 MMA per dx tap instead of the N = 192 stack (A/B of the descriptor model).
+// bit 2: one N = 64 MMA per dx tap instead of the N = 192 stack (A/B of the descriptor model); bits 3-5 timing experiments; bit 6: ignore
+// the workspace (atomics straight into dW); bit 7: the stride-2 / transposed forms stay on the cp.async kernel (conv_wgrad_tc.cu, SW = 2).
 void nnd_conv_set_wgrad_tma(int mode) { g_wgrad_tma = mode; }
 // bit 0: launches the tcgen05 tile kernel serves (conv_tc.cu: 128-channel stride-1 layers, small volumes, >= 4-tap stride-2 dgrad classes)
 // take its TMA-fed variant (conv_tct.cu); bit 1: the same for the stride-2 forms (conv_tc.cu S2 = 1)
@@ -178,7 +184,7 @@ int nnd_conv_trace_dump(const char* path) {
 
 // Dry-run dispatch queries (host only, no CUDA call -- usable without a GPU): which kernel would serve this launch under the current
 // switches.  gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2; wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
-// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2, 6 conv_wgrad_tma.  Negative: bad geometry.
+// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2, 6 conv_wgrad_tma, 8 conv_wgrad_tma_s2.  Negative: bad geometry.
 int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
                              int has_bias, int has_residual, int has_stats) {
   ConvGeom g;
@@ -206,6 +212,7 @@ int nnd_conv_wgrad_dispatch(const int* geom, int Cdy, int Cx) {
   if (g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) return 4;
   if (g_wgrad_tc && (g_wgrad_tma & 1) && nnd_conv_wgrad_tma_supported(g, Cdy, Cx)) return 6;
   if (g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) return 2;
+  if (g_wgrad_tc && g_wgrad_strided && (g_wgrad_tma & 1) && !(g_wgrad_tma & 128) && nnd_conv_wgrad_tma_s2_supported(g, Cdy, Cx)) return 8;
   if (g_wgrad_tc && g_wgrad_strided && nnd_conv_wgrad_tc_strided_supported(g, Cdy, Cx)) return 5;
   return nnd_conv_wgrad_halo_supported(g, Cdy, Cx) ? 1 : 0;
 }
@@ -292,7 +299,9 @@ int nnd_conv_upconv_bf16(const void* x, const void* w_packed, int N, int D, int 
 long long nnd_conv_wgrad_workspace_bytes(const int* geom, int Cdy, int Cx, int Cout, int Cin) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return 0;
-  if (nnd_conv_wgrad_dispatch(geom, Cdy, Cx) != 6) return 0;
+  const int code = nnd_conv_wgrad_dispatch(geom, Cdy, Cx);
+  if (code == 8) return nnd_conv_wgrad_tma_s2_workspace(g, Cdy, Cx, Cout, Cin);
+  if (code != 6) return 0;
   return nnd_conv_wgrad_tma_workspace(g, Cdy, Cx, Cout, Cin);
 }
 
@@ -324,6 +333,16 @@ int nnd_conv_wgrad_bf16_ws(const void* dy, int Cdy, const void* x, int Cx, const
                              (g_wgrad_tma & 64) ? nullptr : ws, ws_bytes, st);
     }
     if (r != NND_ERR_ARG) return r;          // NND_ERR_ARG: no tensor map for this shape -> the cp.async kernels below
+  }
+  if (!g_force_igemm && g_wgrad_tc && g_wgrad_tc != 4 && g_wgrad_strided && (g_wgrad_tma & 1) && !(g_wgrad_tma & 128) &&
+      !nnd_conv_wgrad_tc_supported(g, Cdy, Cx) && nnd_conv_wgrad_tma_s2_supported(g, Cdy, Cx)) {
+    int r;
+    {
+      TraceScope ts("wgrad", "wgrad_tma_s2", g, Cx, Cdy, st);
+      r = nnd_conv_wgrad_tma_s2((const __nv_bfloat16*)dy, Cdy, (const __nv_bfloat16*)x, Cx, g, dw, s_co, s_ci, s_tap, Cout, Cin, g_wgrad_tma,
+                                (g_wgrad_tma & 64) ? nullptr : ws, ws_bytes, st);
+    }
+    if (r != NND_ERR_ARG) return r;
   }
   const char* wk = "wgrad_generic";
   if (!g_force_igemm && g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) wk = "wgrad_tcn";

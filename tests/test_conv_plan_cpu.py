@@ -302,10 +302,10 @@ def test_dispatch_table_of_the_luna_train_step():
     for l in (1, 2, 3, 4):
         assert by[f"decoder.up.P{l}"][5] == "conv_pw (TMA)"                                     # whole up-convolution in one launch
     for l in (1, 2, 3, 4):
-        assert by[f"encoder.stage{l}.conv1"][5] == "conv_tct S2 (TMA)" and by[f"encoder.stage{l}.conv1"][7] == "conv_wgrad_tc SW=2"
+        assert by[f"encoder.stage{l}.conv1"][5] == "conv_tct S2 (TMA)" and by[f"encoder.stage{l}.conv1"][7] == "conv_wgrad_tma S2 (TMA)"
         assert by[f"encoder.stage{l}.conv1"][6] == "conv_pw (TMA)+conv_tct (TMA)"     # stride-2 dgrad: 1-tap class pointwise, 2- / 4- / 8-tap classes tile kernel
     for l in (1, 2, 3, 4):
-        assert by[f"decoder.up.P{l}"][6] == "conv_tct S2 (TMA)" and by[f"decoder.up.P{l}"][7] == "conv_wgrad_tc SW=2"
+        assert by[f"decoder.up.P{l}"][6] == "conv_tct S2 (TMA)" and by[f"decoder.up.P{l}"][7] == "conv_wgrad_tma S2 (TMA)"
     assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")         # stride-1 layers untouched
     _, _, frac_after = dr.report("luna", experimental=False, quiet=True)
     assert frac_after == frac                                                                      # switches restored

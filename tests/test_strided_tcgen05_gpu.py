@@ -41,6 +41,7 @@ def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
     res, kernels = {}, {}
     lib = L.lib()
     try:
+        ops.set_wgrad_tma(1 | 128)               # this test covers the cp.async kernel; its TMA-fed successor: tests/test_wgrad_tma_gpu.py
         for mode in (1, 0):
             ops.set_wgrad_strided_tc(bool(mode))
             mine.zero_grad(set_to_none=True)
@@ -54,6 +55,7 @@ def test_strided_wgrad_on_tcgen05(cin, cout, s, shape):
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
         ops.set_wgrad_strided_tc(True)
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
     assert kernels[1] == ["wgrad_tc_s2"] and kernels[0] != ["wgrad_tc_s2"]
     assert rel_err(res[1], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[1], res[0]) < 1e-3
@@ -75,6 +77,7 @@ def test_transposed_conv_wgrad_on_tcgen05(cin, cout, s, shape):
     yr.backward(gy)
     res, kernels = {}, {}
     try:
+        ops.set_wgrad_tma(1 | 128)               # the cp.async kernel (see above)
         for mode in (True, False):
             ops.set_wgrad_strided_tc(mode)
             mine.zero_grad(set_to_none=True)
@@ -87,6 +90,7 @@ def test_transposed_conv_wgrad_on_tcgen05(cin, cout, s, shape):
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
         ops.set_wgrad_strided_tc(True)
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
     assert kernels[True] == ["wgrad_tc_s2"] and len(kernels[False]) == (8 if s == 2 else 4)
     assert rel_err(res[True], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[True], res[False]) < 1e-3

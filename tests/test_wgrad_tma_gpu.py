@@ -90,3 +90,69 @@ def test_descriptor_model_base_offset_must_stay_zero():
     finally:
         ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
     assert err[1] < 1e-4 and err[5] < 1e-4 and err[3] > 0.5
+
+
+def _module_wgrad(ops, mine, x, gy, mode):
+    ops.set_wgrad_tma(mode)
+    mine.zero_grad(set_to_none=True)
+    xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    ops.trace_start()
+    mine(xm).backward(gy.cuda().to(torch.bfloat16))
+    with tempfile.TemporaryDirectory() as td:
+        ops.trace_dump(os.path.join(td, "t.csv"))
+        kernels = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv"))) if r["kind"] == "wgrad"]
+    return mine.conv.weight.grad.cpu().clone(), kernels
+
+
+@pytest.mark.parametrize("cin,cout,s,shape", [
+    (32, 64, 2, (2, 12, 16, 40)),           # the first encoder stride: 32-channel x (SWIZZLE_64B planes), paired filter rows +1 / -1
+    (64, 128, (1, 2, 2), (2, 6, 12, 12)),   # LIDC-style first stride (unstrided depth), 6 outputs per row: narrow units
+    (128, 256, 2, (1, 8, 10, 34)),          # two co tiles, two 64-channel blocks per CTA, odd output width (17)
+    (256, 320, 2, (2, 8, 8, 8)),            # three co tiles (the last one half empty), two ci tiles
+    (32, 64, 2, (1, 9, 11, 13)),            # odd input sizes in every axis
+    (64, 64, 2, (2, 8, 16, 32)),            # 64 -> 64: pair mode with one 64-channel block
+])
+def test_strided_wgrad_tma_vs_oracle_and_cp_async_kernel(cin, cout, s, shape):
+    """conv_wgrad_tma_s2.cu: x through element-stride-2 tensor maps (odd / even planes), dx = -1 / +1 as one MMA.  fp32 dW against the CPU
+    oracle on bf16-exact operands and against the cp.async kernel (conv_wgrad_tc.cu, SW = 2: accumulation order only)."""
+    from nndetection_b200.arch import conv_ops as ops
+    from test_net_gpu import make_pair
+    mine, ref = make_pair("instance", cin, cout, 3, s, norm=False)
+    g = torch.Generator().manual_seed(91)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    try:
+        new, k_new = _module_wgrad(ops, mine, x, gy, 1)
+        old, k_old = _module_wgrad(ops, mine, x, gy, 1 | 128)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+    assert k_new == ["wgrad_tma_s2"] and k_old == ["wgrad_tc_s2"]
+    assert rel_err(new, ref.conv.weight.grad) < 5e-3            # dy passes through one bf16 rounding on the device
+    assert rel_err(new, old) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,s,shape", [(64, 32, 2, (2, 4, 6, 40)), (128, 64, 2, (1, 5, 3, 9)), (128, 128, (1, 2, 2), (1, 4, 4, 4)),
+                                             (128, 128, 2, (2, 2, 2, 2)), (64, 32, 2, (1, 8, 16, 16))])
+def test_transposed_conv_wgrad_tma_vs_oracle_and_cp_async_kernel(cin, cout, s, shape):
+    """Up-convolutions (kernel == stride): ONE strided launch with the operands' roles swapped (dense = the layer input, strided = dy at
+    2 i + {0, 1}: taps dx in {0, +1})."""
+    from nndetection_b200.arch import conv_ops as ops
+    from test_net_gpu import make_pair
+    mine, ref = make_pair("instance", cin, cout, None, s, transposed=True)
+    g = torch.Generator().manual_seed(92)
+    x = q(torch.randn(shape[0], cin, *shape[1:], generator=g))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = q(torch.randn(yr.shape, generator=g))
+    yr.backward(gy)
+    try:
+        new, k_new = _module_wgrad(ops, mine, x, gy, 1)
+        old, k_old = _module_wgrad(ops, mine, x, gy, 1 | 128)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+    assert k_new == ["wgrad_tma_s2"] and k_old == ["wgrad_tc_s2"]
+    assert rel_err(new, ref.conv.weight.grad) < 5e-3
+    assert rel_err(new, old) < 1e-4
