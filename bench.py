@@ -334,6 +334,7 @@ def main():
                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_step": roof_step,
+               "roofline_kernels": kernel_rooflines(dev, bs) if world == 1 else None,
                "train_tflops": 3 * conv_flops_per_patch(arch, patch) * bs * world * args.steps / (ms / 1e3) / 1e12}
         try:
             out["nms"] = nms_rates(dev)
@@ -408,6 +409,58 @@ def conv_roofline(net, dev, arch, patch, bs):
             "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "algorithmic_bytes_per_launch": 2.0 * vox * (cin + cout) + 2.0 * 27 * cin * cout, "traffic": traffic,
             "traffic_source": "profiles/r01_ncu_conv_tcs32_summary.txt (ncu --set full, same layer and shape)" if luna_shape else None}
+
+
+def kernel_rooflines(dev, bs):
+    """The other tensor-core kernels of the step, each on its largest layer of the LUNA plan, launched in isolation (CUDA events on the
+    launch stream, 2 warm-ups + 5 timed launches): TFLOP/s against the measured burst bf16 peak.  `roofline` above stays the single
+    largest launch; `roofline_step` is the whole step."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.arch.conv import ConvInstanceRelu
+    hbm, tf_burst, tf_sus, kind = peaks()
+    cases = [  # kind, cin, cout, input size, stride
+        ("fprop", 128, 128, 32, 1), ("wgrad", 128, 128, 32, 1), ("wgrad", 64, 64, 64, 1), ("wgrad", 32, 32, 128, 1),
+        ("fprop", 32, 64, 128, 2), ("wgrad", 32, 64, 128, 2), ("fprop", 64, 64, 64, 1),
+    ]
+    out = []
+    for what, cin, cout, size, stride in cases:
+        try:
+            layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=stride, padding=1).to(dev)
+            x = torch.randn(bs, cin, size, size, size, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+            plan = layer.plan(bs, (size,) * 3)
+            wp, _ = layer.packed()
+            y = ops.empty_cl(bs, cout, plan.out_sp, device=dev)
+            y.normal_()
+            st = torch.zeros((2, bs, cout), dtype=torch.float32, device=dev)
+            dw = torch.zeros_like(layer.conv.weight)
+            if what == "fprop":
+                fn = lambda: ops.conv_gather(x, wp, plan.fprop[0], y, cout, cout, stat_sum=st[0], stat_sq=st[1])
+            else:
+                fn = lambda: ops.conv_wgrad(y, cout, x, cin, plan.wgrad[0], dw, cin * 27, 27, 1, cout, cin)
+            ops.trace_start()
+            fn()
+            import tempfile, csv
+            with tempfile.TemporaryDirectory() as td:
+                ops.trace_dump(os.path.join(td, "t.csv"))
+                kern = [r["kernel"] for r in csv.DictReader(open(os.path.join(td, "t.csv")))][-1]
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            vo = bs * plan.out_sp[0] * plan.out_sp[1] * plan.out_sp[2]
+            fl = 2.0 * 27 * cin * cout * vo
+            out.append({"kernel": kern, "pass": what, "layer": f"{cin}->{cout} 3x3x3 stride {stride} @ {size}^3 x batch {bs}", "ms_per_launch": ms,
+                        "achieved": fl / ms / 1e9, "unit": "TFLOP/s", "peak": tf_burst, "frac": fl / ms / 1e9 / tf_burst,
+                        "algorithmic_flops_per_launch": fl})
+            del layer, x, y, dw
+        except Exception as e:                      # a comparator table: never fail the bench line over it
+            out.append({"pass": what, "layer": f"{cin}->{cout} stride {stride} @ {size}^3", "error": repr(e)})
+    return out
 
 
 def _nms_stress(n, dev):

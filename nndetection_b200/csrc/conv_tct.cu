@@ -120,8 +120,9 @@ conv_tct_kernel(const __grid_constant__ TctMaps maps, const ConvGeom g, const Co
 
   if (warp == 0) {
     // ================================================================ producer: one lane, a flat sequence of chunks = (tile, CK-channel
-    // block); a chunk = its halo planes + NI_ITEMS weight items.  The halo of the NEXT chunk is posted in the middle of the current
-    // one, so it has landed long before its first tap is due.
+    // block); a chunk = its halo planes + NI_ITEMS weight items.  The halo of the NEXT chunk is posted right behind the first weight
+    // item of the current one (its stage was released by the chunk before): a whole chunk of MMAs hides the load -- for the stride-2
+    // form (90 KB of planes per 16-channel chunk against ~2.6 k cycles of MMAs) half a chunk did not.
     if (lane == 0) {
       unsigned slot = 0, slot_phase = 0, astage = 0, a_phase = 0;
       const int my_tiles = (tl.total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -146,7 +147,7 @@ conv_tct_kernel(const __grid_constant__ TctMaps maps, const ConvGeom g, const Co
         const int nt = tile % tl.NT;
         if (chunk == 0) load_halo(0);
         for (int it = 0; it < NI_ITEMS; ++it) {
-          if (it == NI_ITEMS / 2 && chunk + 1 < n_chunks) load_halo(chunk + 1);
+          if (it == (NI_ITEMS > 1 ? 1 : 0) && chunk + 1 < n_chunks) load_halo(chunk + 1);
           mbar_wait(EMPTYB(slot), slot_phase ^ 1);
           const unsigned b_base = smem_u32(sB + (size_t)slot * B_BYTES);
           tct_expect_tx(FULLB(slot), B_BYTES);

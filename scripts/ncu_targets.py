@@ -2,6 +2,7 @@
     python scripts/ncu_targets.py pw    cin cout size batch      # 1x1x1 lateral (conv_pw / conv_igemm), forward
     python scripts/ncu_targets.py up    cin cout size batch      # kernel == stride 2 up-convolution + lateral add, forward (size = input)
     python scripts/ncu_targets.py block cin cout size batch      # 3x3x3 conv + instance norm + ReLU, forward + backward (conv, wgrad, norm kernels)
+    python scripts/ncu_targets.py block2 cin cout size batch     # the same with stride 2 (size = input size)
     python scripts/ncu_targets.py nms   n                        # one nndet._C.nms call on the SURVEY 8d stress boxes (mask + scan kernels)
 env NND_PW=0: pointwise forms on the mma.sync gather kernel (A/B)."""
 import os
@@ -41,10 +42,11 @@ elif mode == "up":
     with torch.no_grad():
         for _ in range(REPS):
             y = layer(x, residual=lat)
-elif mode == "block":
-    layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=1, padding=1).to(dev)
+elif mode in ("block", "block2"):              # block2: the stride-2 form (size = input size)
+    stride = 2 if mode == "block2" else 1
+    layer = ConvInstanceRelu(3, cin, cout, kernel_size=3, stride=stride, padding=1).to(dev)
     x = rnd(cin, size).requires_grad_(True)
-    gy = rnd(cout, size)
+    gy = rnd(cout, size // stride)
     for _ in range(REPS):
         layer.zero_grad(set_to_none=True)
         layer(x).backward(gy)
