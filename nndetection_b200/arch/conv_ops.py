@@ -166,13 +166,28 @@ def tc_bulk_enabled() -> bool:
     return _TC_BULK
 
 
+_WGRAD_WS = {}          # (device index, stream handle) -> uint8 workspace tensor, grown on demand
+
+
+def _wgrad_workspace(nbytes: int, device) -> Tensor:
+    """Split-K partials of the TMA-fed wgrad kernels: ONE buffer per (device, launch stream), grown to the largest request and kept --
+    consecutive launches of a stream reuse it in stream order (the finishing pass of a launch runs before the next launch's kernel), and
+    the ~40 allocations / frees per step it replaces no longer churn the caching allocator (a first-time cudaMalloc inside a step costs
+    ~10 ms).  Still allocated through torch: the planner's VRAM estimator sees the bytes."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _WGRAD_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WGRAD_WS[key] = ws
+    return ws
+
+
 def conv_wgrad(dy: Tensor, cdy: int, x: Tensor, cx: int, geom, dw: Tensor, s_co: int, s_ci: int, s_tap: int, cout: int,
                cin: int):
     lib = L.lib()
     lib.nnd_conv_wgrad_workspace_bytes.restype = c_longlong
     nbytes = int(lib.nnd_conv_wgrad_workspace_bytes(geom, c_int(cdy), c_int(cx), c_int(cout), c_int(cin)))
-    # split-K partials of the TMA-fed kernel: from the caching allocator on the launch stream (freed behind the launch in stream order)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device) if nbytes > 0 else None
+    ws = _wgrad_workspace(nbytes, dy.device) if nbytes > 0 else None
     L.check(lib.nnd_conv_wgrad_bf16_ws(L.ptr(dy), c_int(cdy), L.ptr(x), c_int(cx), geom, L.ptr(dw), c_longlong(s_co),
                                        c_longlong(s_ci), c_longlong(s_tap), c_int(cout), c_int(cin), L.ptr(ws), c_longlong(nbytes),
                                        L.stream_ptr()), "nnd_conv_wgrad_bf16_ws")

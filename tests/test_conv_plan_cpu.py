@@ -331,3 +331,29 @@ def test_item_order_weight_pack_layout():
         sl = dst[start:start + n_tile * kg].reshape(kg, n_tile, 8)                                # what one bulk copy lands in smem
         want = src[t_, nt_ * n_tile:(nt_ + 1) * n_tile, kc_ * kg:(kc_ + 1) * kg].transpose(1, 0, 2)   # [k group][n][8] of that tap / chunk / tile
         assert np.array_equal(sl, want)
+
+
+def test_split_k_plan_of_the_tma_weight_gradients():
+    """Host-only: the workspace the TMA-fed wgrad kernels ask for = splits x taps x Cout x Cin fp32 partials, i.e. the split-K plan
+    (csrc/conv_wgrad_tma.cu:wm_plan, conv_wgrad_tma_s2.cu:ws_plan): one CTA group per filter row -- per PAIR of rows when dy has 64
+    channels (rows (dy, dy - 1) at stride 1, (+1, -1) at stride 2) --, one wave of 148 SMs, >= 2 units per split."""
+    from ctypes import c_int, c_longlong
+    from nndetection_b200 import _lib as L
+    lib = L.lib()
+    lib.nnd_conv_wgrad_workspace_bytes.restype = c_longlong
+
+    def splits(cin, cout, in_sp, s, n=4):
+        plan = ConvPlan(n, cin, cout, in_sp, 3, s, 1, False)
+        code = lib.nnd_conv_wgrad_dispatch(plan.wgrad[0], c_int(cout), c_int(cin))
+        b = int(lib.nnd_conv_wgrad_workspace_bytes(plan.wgrad[0], c_int(cout), c_int(cin), c_int(cout), c_int(cin)))
+        assert b % (27 * cout * cin * 4) == 0
+        return code, b // (27 * cout * cin * 4)
+
+    assert splits(128, 128, (32, 32, 32), 1) == (6, 16)          # 9 filter rows x 1 co tile x 1 ci tile -> 148 // 9 = 16 splits
+    assert splits(64, 64, (64, 64, 64), 1) == (6, 24)            # 64-channel dy: 6 paired groups -> 24 splits
+    assert splits(256, 256, (16, 16, 16), 1) == (6, 4)           # 9 rows x 2 co tiles x 2 ci tiles = 36 CTAs per split
+    assert splits(320, 320, (8, 8, 8), 1) == (6, 1)              # 9 x 3 x 5 = 135 tiles: no split
+    assert splits(32, 64, (128, 128, 128), 2) == (8, 24)         # stride 2, 64-channel dy: rows (+1, -1) paired, row 0 alone: 6 groups
+    assert splits(64, 128, (64, 64, 64), 2) == (8, 16)           # 9 groups
+    assert splits(32, 32, (128, 128, 128), 1)[0] == 3            # 32-channel layers stay on the stacked-tap kernel (no workspace)
+    assert splits(128, 128, (4, 4, 4), 1)[1] >= 1                # 4^3 level: boxes larger than the tensor, still planned
