@@ -39,6 +39,10 @@ int nnd_conv_wgrad_tma(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x,
                        long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
                        cudaStream_t st);
 long long nnd_conv_wgrad_tma_workspace(const ConvGeom& g, int Cdy, int Cx, int Cout, int Cin);
+int nnd_conv_wgrad_tma32_supported(const ConvGeom& g, int Cdy, int Cx);
+long long nnd_conv_wgrad_tma32_workspace(const ConvGeom& g, int Cout, int Cin);
+int nnd_conv_wgrad_tma32(const __nv_bfloat16* dy, const __nv_bfloat16* x, const ConvGeom& g, float* dw, long long s_co, long long s_ci,
+                         long long s_tap, int Cout, int Cin, void* ws, long long ws_bytes, cudaStream_t st);
 int nnd_conv_wgrad_tma_s2_supported(const ConvGeom& g, int Cdy, int Cx);
 int nnd_conv_wgrad_tma_s2(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16* x, int Cx, const ConvGeom& g, float* dw,
                           long long s_co, long long s_ci, long long s_tap, int Cout, int Cin, int mode, void* ws, long long ws_bytes,
@@ -139,7 +143,8 @@ void nnd_conv_set_pointwise_tma(int enable) { g_pw = enable; }
 // bit 0: stride-1 3x3x3 / 1x3x3 weight gradients with channel counts in multiples of 64 take the TMA-fed kernel of conv_wgrad_tma.cu
 // instead of the cp.async one (conv_wgrad_tc.cu); bit 1: descriptors carry base_offset = (start >> 7) & 7 for row-shifted starts;
 // bit 2: one N = 64 MMA per dx tap instead of the N = 192 stack (A/B of the descriptor model); bits 3-5 timing experiments; bit 6: ignore
-// the workspace (atomics straight into dW); bit 7: the stride-2 / transposed forms stay on the cp.async kernel (conv_wgrad_tc.cu, SW = 2).
+// the workspace (atomics straight into dW); bit 7: the stride-2 / transposed forms stay on the cp.async kernel (conv_wgrad_tc.cu, SW = 2);
+// bit 8: the 32 -> 32 layers stay on the cp.async stacked-tap kernel (conv_wgrad_tc32.cu).
 void nnd_conv_set_wgrad_tma(int mode) { g_wgrad_tma = mode; }
 // bit 0: launches the tcgen05 tile kernel serves (conv_tc.cu: 128-channel stride-1 layers, small volumes, >= 4-tap stride-2 dgrad classes)
 // take its TMA-fed variant (conv_tct.cu); bit 1: the same for the stride-2 forms (conv_tc.cu S2 = 1)
@@ -184,7 +189,7 @@ int nnd_conv_trace_dump(const char* path) {
 
 // Dry-run dispatch queries (host only, no CUDA call -- usable without a GPU): which kernel would serve this launch under the current
 // switches.  gather: 0 conv_igemm (mma.sync), 1 conv_tc, 2 conv_tcs, 3 conv_tc S2; wgrad: 0 generic, 1 halo (mma.sync), 2 conv_wgrad_tc,
-// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2, 6 conv_wgrad_tma, 8 conv_wgrad_tma_s2.  Negative: bad geometry.
+// 3 conv_wgrad_tc32, 4 conv_wgrad_tcn, 5 conv_wgrad_tc SW=2, 6 conv_wgrad_tma, 8 conv_wgrad_tma_s2, 9 conv_wgrad_tma32.  Negative: bad geometry.
 int nnd_conv_gather_dispatch(const int* geom, long long out_n_stride, long long out_v_stride, int out_fp32, int Cout, int CoutPad,
                              int has_bias, int has_residual, int has_stats) {
   ConvGeom g;
@@ -208,7 +213,8 @@ int nnd_conv_wgrad_dispatch(const int* geom, int Cdy, int Cx) {
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return -1;
   if (g_force_igemm) return 0;
-  if (g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) return 3;
+  if (g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g)))
+    return ((g_wgrad_tma & 1) && !(g_wgrad_tma & 256) && nnd_conv_wgrad_tma32_supported(g, Cdy, Cx)) ? 9 : 3;
   if (g_wgrad_tc == 4 && nnd_conv_wgrad_tcn_supported(g, Cdy, Cx)) return 4;
   if (g_wgrad_tc && (g_wgrad_tma & 1) && nnd_conv_wgrad_tma_supported(g, Cdy, Cx)) return 6;
   if (g_wgrad_tc && nnd_conv_wgrad_tc_supported(g, Cdy, Cx)) return 2;
@@ -301,6 +307,7 @@ long long nnd_conv_wgrad_workspace_bytes(const int* geom, int Cdy, int Cx, int C
   if (parse_geom(geom, g) != NND_OK) return 0;
   const int code = nnd_conv_wgrad_dispatch(geom, Cdy, Cx);
   if (code == 8) return nnd_conv_wgrad_tma_s2_workspace(g, Cdy, Cx, Cout, Cin);
+  if (code == 9) return nnd_conv_wgrad_tma32_workspace(g, Cout, Cin);
   if (code != 6) return 0;
   return nnd_conv_wgrad_tma_workspace(g, Cdy, Cx, Cout, Cin);
 }
@@ -319,6 +326,15 @@ int nnd_conv_wgrad_bf16_ws(const void* dy, int Cdy, const void* x, int Cx, const
   ConvGeom g;
   if (parse_geom(geom, g) != NND_OK) return NND_ERR_ARG;
   if (!g_force_igemm && g_wgrad_tc && nnd_conv_wgrad_tc32_supported(g, Cdy, Cx) && (g_wgrad_tc == 2 || nnd_conv_wgrad_tc32_profitable(g))) {
+    if ((g_wgrad_tma & 1) && !(g_wgrad_tma & 256) && nnd_conv_wgrad_tma32_supported(g, Cdy, Cx)) {
+      int r;
+      {
+        TraceScope ts("wgrad", "wgrad_tma32", g, Cx, Cdy, st);
+        r = nnd_conv_wgrad_tma32((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, g, dw, s_co, s_ci, s_tap, Cout, Cin,
+                                 (g_wgrad_tma & 64) ? nullptr : ws, ws_bytes, st);
+      }
+      if (r != NND_ERR_ARG) return r;          // NND_ERR_ARG: no tensor map -> the cp.async kernel below
+    }
     TraceScope ts("wgrad", "wgrad_tc32", g, Cx, Cdy, st);
     return nnd_conv_wgrad_tc32((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, g, dw, s_co, s_ci, s_tap, Cout, Cin, st);
   }

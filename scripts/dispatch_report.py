@@ -15,7 +15,7 @@ import numpy as np  # noqa: E402
 
 GATHER = {0: "conv_igemm (mma.sync)", 1: "conv_tc", 2: "conv_tcs", 3: "conv_tc S2", 4: "conv_pw (TMA)", 6: "conv_tct (TMA)", 7: "conv_tct S2 (TMA)"}
 WGRAD = {0: "wgrad generic (mma.sync)", 1: "wgrad halo (mma.sync)", 2: "conv_wgrad_tc", 3: "conv_wgrad_tc32", 4: "conv_wgrad_tcn",
-         5: "conv_wgrad_tc SW=2", 6: "conv_wgrad_tma (TMA)", 8: "conv_wgrad_tma S2 (TMA)"}
+         5: "conv_wgrad_tc SW=2", 6: "conv_wgrad_tma (TMA)", 8: "conv_wgrad_tma S2 (TMA)", 9: "conv_wgrad_tma32 (TMA)"}
 
 
 def pad32(c):

@@ -288,7 +288,7 @@ def test_dispatch_table_of_the_luna_train_step():
     rows, totals, frac = dr.report("luna", experimental=False, quiet=True)
     by = {r[0]: r for r in rows}
     assert abs(sum(totals.values()) - 8242) < 15 and 0.89 < frac < 0.94
-    assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")
+    assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tma32 (TMA)")
     # 128 -> 128: TMA-fed tile kernel (fprop + dgrad) and TMA-fed wgrad (defaults since round 2)
     assert by["encoder.stage2.conv2"][5:8] == ("conv_tct (TMA)", "conv_tct (TMA)", "conv_wgrad_tma (TMA)")
     assert by["encoder.stage1.conv2"][7] == "conv_wgrad_tma (TMA)" and by["head.regressor.c_in@P3"][7] == "conv_wgrad_tma (TMA)"
@@ -306,7 +306,7 @@ def test_dispatch_table_of_the_luna_train_step():
         assert by[f"encoder.stage{l}.conv1"][6] == "conv_pw (TMA)+conv_tct (TMA)"     # stride-2 dgrad: 1-tap class pointwise, 2- / 4- / 8-tap classes tile kernel
     for l in (1, 2, 3, 4):
         assert by[f"decoder.up.P{l}"][6] == "conv_tct S2 (TMA)" and by[f"decoder.up.P{l}"][7] == "conv_wgrad_tma S2 (TMA)"
-    assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tc32")         # stride-1 layers untouched
+    assert by["encoder.stage0.conv2"][5:8] == ("conv_tcs", "conv_tcs", "conv_wgrad_tma32 (TMA)")  # stride-1 layers untouched
     _, _, frac_after = dr.report("luna", experimental=False, quiet=True)
     assert frac_after == frac                                                                      # switches restored
 
@@ -355,5 +355,5 @@ def test_split_k_plan_of_the_tma_weight_gradients():
     assert splits(320, 320, (8, 8, 8), 1) == (6, 1)              # 9 x 3 x 5 = 135 tiles: no split
     assert splits(32, 64, (128, 128, 128), 2) == (8, 24)         # stride 2, 64-channel dy: rows (+1, -1) paired, row 0 alone: 6 groups
     assert splits(64, 128, (64, 64, 64), 2) == (8, 16)           # 9 groups
-    assert splits(32, 32, (128, 128, 128), 1)[0] == 3            # 32-channel layers stay on the stacked-tap kernel (no workspace)
+    assert splits(32, 32, (128, 128, 128), 1) == (9, 148)        # 32-channel layers: TMA-fed stacked-tap kernel, one partial block per CTA
     assert splits(128, 128, (4, 4, 4), 1)[1] >= 1                # 4^3 level: boxes larger than the tensor, still planned

@@ -156,3 +156,34 @@ def test_transposed_conv_wgrad_tma_vs_oracle_and_cp_async_kernel(cin, cout, s, s
     assert k_new == ["wgrad_tma_s2"] and k_old == ["wgrad_tc_s2"]
     assert rel_err(new, ref.conv.weight.grad) < 5e-3
     assert rel_err(new, old) < 1e-4
+
+
+@pytest.mark.parametrize("sp,bs,k", [((12, 16, 40), 2, 3), ((5, 9, 20), 1, 3), ((16, 32, 48), 4, 3), ((4, 24, 16), 1, (1, 3, 3))])
+def test_32_channel_stacked_tap_wgrad_tma_vs_oracle_and_cp_async_kernel(sp, bs, k):
+    """conv_wgrad_tma32.cu (all 27 taps per CTA: dy slices stacked along M, x rows along N through descriptor strides of two SWIZZLE_64B
+    tensor-map boxes per tile) against the fp32 CPU oracle and against conv_wgrad_tc32.cu; ragged tiles in every axis, a 1x3x3 filter,
+    workspace (split-K partials per CTA) and atomics epilogue."""
+    from ctypes import c_int
+    from nndetection_b200 import _lib as L
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.arch.conv import ConvInstanceRelu
+    pad = 1 if isinstance(k, int) else tuple(v // 2 for v in k)
+    layer = ConvInstanceRelu(3, 32, 32, kernel_size=k, stride=1, padding=pad).cuda()
+    g = torch.Generator().manual_seed(95 + sp[2])
+    x = q(torch.randn(bs, 32, *sp, generator=g))
+    dy = q(torch.randn(bs, 32, *sp, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, tuple(layer.conv.weight.shape), dy, stride=1, padding=pad)
+    xm = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    dym = dy.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    res = {}
+    try:
+        L.lib().nnd_conv_set_wgrad_tc(c_int(2))             # the stacked-tap kernels also on volumes too small to fill the grid
+        for mode in (1, 1 | 64, 1 | 256):                   # TMA + workspace | TMA + atomics | cp.async kernel
+            ops.set_wgrad_tma(mode)
+            res[mode] = _wgrad(ops, layer, xm, dym, 32, 32, sp, bs)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+        L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+    assert res[1][1] == ["wgrad_tma32"] and res[1 | 64][1] == ["wgrad_tma32"] and res[1 | 256][1] == ["wgrad_tc32"]
+    assert rel_err(res[1][0], ref) < 1e-4 and rel_err(res[1 | 64][0], ref) < 1e-4
+    assert rel_err(res[1][0], res[1 | 256][0]) < 1e-4
