@@ -187,3 +187,24 @@ def test_32_channel_stacked_tap_wgrad_tma_vs_oracle_and_cp_async_kernel(sp, bs, 
     assert res[1][1] == ["wgrad_tma32"] and res[1 | 64][1] == ["wgrad_tma32"] and res[1 | 256][1] == ["wgrad_tc32"]
     assert rel_err(res[1][0], ref) < 1e-4 and rel_err(res[1 | 64][0], ref) < 1e-4
     assert rel_err(res[1][0], res[1 | 256][0]) < 1e-4
+
+
+def test_32_channel_wgrad_at_full_resolution_matches_the_cp_async_kernel():
+    """The layer the kernel exists for (32 -> 32 @128^3, batch 4: 32 768 tiles over 148 CTAs) -- too large for the CPU oracle, so the A/B
+    partner is conv_wgrad_tc32.cu (itself pinned on the oracle at small sizes): same products, different summation order."""
+    from nndetection_b200.arch import conv_ops as ops
+    from nndetection_b200.arch.conv import ConvInstanceRelu
+    layer = ConvInstanceRelu(3, 32, 32, kernel_size=3, stride=1, padding=1).cuda()
+    sp, bs = (128, 128, 128), 4
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xm = torch.randn(bs, 32, *sp, generator=g, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    dym = torch.randn(bs, 32, *sp, generator=g, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    res = {}
+    try:
+        for mode in (1, 1 | 256):
+            ops.set_wgrad_tma(mode)
+            res[mode] = _wgrad(ops, layer, xm, dym, 32, 32, sp, bs)
+    finally:
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
+    assert res[1][1] == ["wgrad_tma32"] and res[1 | 256][1] == ["wgrad_tc32"]
+    assert rel_err(res[1][0], res[1 | 256][0]) < 1e-4
