@@ -393,6 +393,7 @@ def test_stacked_tap_wgrad_32_channels(shape):
     yr.backward(gy)
     res = {}
     try:
+        ops.set_wgrad_tma(1 | 256)               # this test covers the cp.async kernel; its TMA-fed successor: tests/test_wgrad_tma_gpu.py
         for mode in (2, 0):
             L.lib().nnd_conv_set_wgrad_tc(c_int(mode))
             mine.zero_grad(set_to_none=True)
@@ -401,6 +402,7 @@ def test_stacked_tap_wgrad_32_channels(shape):
             res[mode] = mine.conv.weight.grad.cpu().clone()
     finally:
         L.lib().nnd_conv_set_wgrad_tc(c_int(1))
+        ops.set_wgrad_tma(ops.WGRAD_TMA_DEFAULT)
     assert rel_err(res[2], ref.conv.weight.grad) < 5e-3
     assert rel_err(res[2], res[0]) < 1e-3
 
