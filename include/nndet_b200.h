@@ -193,6 +193,14 @@ int nnd_seg_loss_bwd(const float* logits, const float* target, const double* sum
 int nnd_seg_conv_bwd(const void* x, int C, const float* w, const float* dlogits, long long total, void* dx, float* dw, float* db,
                      cudaStream_t stream);
 
+/* ---- host-only plan queries of the TMA-fed kernels (no CUDA call; tests/test_tma_plan_cpu.py replays them in numpy): flat int tables,
+ *      return = ints written or -1.  conv_tct: [n_planes, a_stage_bytes, a_bytes, ROWB, per plane pd,ph,pw,cd,ch,cw,base,box_w,box_h,box_d,
+ *      per tap tap_off,tap_sbo,slice_step]; wgrad: [narrow,bw,bh,pair,nb,(cb,)HB,WS,n_groups,ci_tiles,splits,units_per_split,total_units,
+ *      (dxmask,) per group dz,ty,gtw[3],gtw2[3]]. */
+int nnd_conv_tct_plan_debug(const int* geom_host, int mt, int s2, int* out, int cap);
+int nnd_conv_wgrad_tma_plan_debug(const int* geom_host, int Cdy, int Cx, int* out, int cap);
+int nnd_conv_wgrad_tma_s2_plan_debug(const int* geom_host, int Cdy, int Cx, int* out, int cap);
+
 /* ---- TMA-fed pointwise GEMM (csrc/conv_pw.cu).  nnd_conv_set_pointwise_tma(1): single-tap launches of nnd_conv_gather_bf16 (1x1x1
  *      convolutions = U-FPN laterals, nndet/arch/decoder/base.py:216-241, their dgrad, parity classes of up-convolutions) take it.
  *      nnd_conv_upconv_bf16: a whole kernel == stride nn.ConvTranspose3d (decoder/base.py:272-304) in one launch; x bf16 [N,D,H,W,Cin],

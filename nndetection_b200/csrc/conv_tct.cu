@@ -336,19 +336,19 @@ AxisPlanes axis_planes(int stride, int n) {
   return a;
 }
 
-template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2>
-int launch_tct(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
-  constexpr int CK = S2 ? 16 : 32, ROWB = CK * 2;
-  const TctEncodeTiledFn enc = tct_encode_fn();
-  if (!enc) return NND_ERR_ARG;
-  if (((size_t)in & 15) || ((size_t)w & 15) || g.T % TG) return NND_ERR_ARG;
+// Host plan of a launch: the halo planes of one channel chunk (entries, first coordinate, byte offset inside a stage, tensor-map box
+// extents) and, per tap, where its 128 operand rows start (byte offset inside a stage), the pitch of its 8-row groups and of its depth
+// slices.  Pure arithmetic: shared by the launcher and by nnd_conv_tct_plan_debug, which tests/test_tma_plan_cpu.py replays in numpy.
+struct TctHostPlan {
   TctArgs tl;
-  tl.DB = (g.Ld + MT - 1) / MT; tl.HB = (g.Lh + TBH - 1) / TBH; tl.WB = (g.Lw + TBW - 1) / TBW; tl.NT = ep.CoutPad / N_TILE;
-  tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
-  if (tl.total <= 0) return NND_OK;
+  int a_stage_bytes;
+  int box[T_MAX_PLANES][3];          // tensor-map box extents (w, h, d) in tensor elements: (entries - 1) * stride + 1
+  int max_tw;
+};
+
+void tct_host_plan(const ConvGeom& g, int MT, int ROWB, TctHostPlan& hp) {
+  TctArgs& tl = hp.tl;
   const AxisPlanes ad = axis_planes(g.sd, MT), ah = axis_planes(g.sh, TBH), aw = axis_planes(g.sw, TBW);
-  TctMaps maps;
-  const CUtensorMapSwizzle swz = S2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
   int plane_of[2][2][2];
   tl.n_planes = 0; tl.a_bytes = 0;
   int off = 0;
@@ -364,20 +364,11 @@ int launch_tct(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
         const int bytes = pl.pd * pl.ph * pl.pw * ROWB;
         tl.a_bytes += bytes;
         off += (bytes + 1023) / 1024 * 1024;
-        const cuuint64_t gdim[5] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di, (cuuint64_t)g.N};
-        const cuuint64_t gstride[4] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wi * g.Cin * 2, (cuuint64_t)g.Hi * g.Wi * g.Cin * 2,
-                                       (cuuint64_t)g.Di * g.Hi * g.Wi * g.Cin * 2};
         // with an element stride s the box spans (entries - 1) * s + 1 tensor elements of which every s-th is copied
-        const cuuint32_t box[5] = {(cuuint32_t)CK, (cuuint32_t)((pl.pw - 1) * g.sw + 1), (cuuint32_t)((pl.ph - 1) * g.sh + 1),
-                                   (cuuint32_t)((pl.pd - 1) * g.sd + 1), 1};
-        const cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
-        if (enc(&maps.pl[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), gdim, gstride, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-          return NND_ERR_ARG;
+        hp.box[p][0] = (pl.pw - 1) * g.sw + 1; hp.box[p][1] = (pl.ph - 1) * g.sh + 1; hp.box[p][2] = (pl.pd - 1) * g.sd + 1;
       }
-  for (int p = tl.n_planes; p < T_MAX_PLANES; ++p) maps.pl[p] = maps.pl[0];
-  const int a_stage_bytes = off;
-  int max_tw = 0;
+  hp.a_stage_bytes = off;
+  hp.max_tw = 0;
   for (int t = 0; t < g.T; ++t) {
     // axis offset -> (plane, shift): unstrided axis: the halo plane at off + 1; strided: off = 0 even plane, off = -1 / +1 odd plane at 0 / 1
     auto pick = [](int stride, int o, int& plane, int& shift) {
@@ -389,11 +380,39 @@ int launch_tct(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& 
     tl.tap_off[t] = pl.base + ((sz * pl.ph + sy) * pl.pw + sx) * ROWB;
     tl.tap_sbo[t] = pl.pw * ROWB;
     tl.slice_step[t] = pl.ph * pl.pw * ROWB;
-    if (g.tap_w[t] > max_tw) max_tw = g.tap_w[t];
+    if (g.tap_w[t] > hp.max_tw) hp.max_tw = g.tap_w[t];
   }
   for (int t = g.T; t < NND_MAX_TAPS; ++t) { tl.tap_off[t] = 0; tl.tap_sbo[t] = 0; tl.slice_step[t] = 0; }
+}
+
+template <int N_TILE, int MT, int TG, int ACC, int B_SLOTS, int S2>
+int launch_tct(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvGeom& g, const ConvEpilogue& ep, cudaStream_t st) {
+  constexpr int CK = S2 ? 16 : 32, ROWB = CK * 2;
+  const TctEncodeTiledFn enc = tct_encode_fn();
+  if (!enc) return NND_ERR_ARG;
+  if (((size_t)in & 15) || ((size_t)w & 15) || g.T % TG) return NND_ERR_ARG;
+  TctHostPlan hp;
+  TctArgs& tl = hp.tl;
+  tl.DB = (g.Ld + MT - 1) / MT; tl.HB = (g.Lh + TBH - 1) / TBH; tl.WB = (g.Lw + TBW - 1) / TBW; tl.NT = ep.CoutPad / N_TILE;
+  tl.total = g.N * tl.DB * tl.HB * tl.WB * tl.NT;
+  if (tl.total <= 0) return NND_OK;
+  tct_host_plan(g, MT, ROWB, hp);
+  TctMaps maps;
+  const CUtensorMapSwizzle swz = S2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+  for (int p = 0; p < tl.n_planes; ++p) {
+    const cuuint64_t gdim[5] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.Di, (cuuint64_t)g.N};
+    const cuuint64_t gstride[4] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wi * g.Cin * 2, (cuuint64_t)g.Hi * g.Wi * g.Cin * 2,
+                                   (cuuint64_t)g.Di * g.Hi * g.Wi * g.Cin * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)CK, (cuuint32_t)hp.box[p][0], (cuuint32_t)hp.box[p][1], (cuuint32_t)hp.box[p][2], 1};
+    const cuuint32_t estr[5] = {1, (cuuint32_t)g.sw, (cuuint32_t)g.sh, (cuuint32_t)g.sd, 1};
+    if (enc(&maps.pl[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(in), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return NND_ERR_ARG;
+  }
+  for (int p = tl.n_planes; p < T_MAX_PLANES; ++p) maps.pl[p] = maps.pl[0];
+  const int a_stage_bytes = hp.a_stage_bytes;
   {
-    const cuuint64_t gdim[2] = {(cuuint64_t)g.Cin, (cuuint64_t)(max_tw + 1) * ep.CoutPad};
+    const cuuint64_t gdim[2] = {(cuuint64_t)g.Cin, (cuuint64_t)(hp.max_tw + 1) * ep.CoutPad};
     const cuuint64_t gstride[1] = {(cuuint64_t)g.Cin * 2};
     const cuuint32_t box[2] = {(cuuint32_t)CK, (cuuint32_t)N_TILE};
     const cuuint32_t estr[2] = {1, 1};
@@ -457,4 +476,36 @@ int nnd_conv_tct_s2(const __nv_bfloat16* in, const __nv_bfloat16* w, const ConvG
   if (ep.CoutPad % 128 == 0) return g3 ? launch_tct<128, 2, 3, 2, 3, 1>(in, w, g, ep, st) : launch_tct<128, 2, 1, 2, 8, 1>(in, w, g, ep, st);
   if (ep.CoutPad % 64 == 0) return g3 ? launch_tct<64, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tct<64, 2, 1, 2, 8, 1>(in, w, g, ep, st);
   return g3 ? launch_tct<32, 2, 3, 2, 4, 1>(in, w, g, ep, st) : launch_tct<32, 2, 1, 2, 8, 1>(in, w, g, ep, st);
+}
+
+// Host-only: the plan of a launch as flat ints (tests/test_tma_plan_cpu.py replays it in numpy against a direct gather).
+//   out = [n_planes, a_stage_bytes, a_bytes, ROWB,  per plane: pd, ph, pw, cd, ch, cw, base, box_w, box_h, box_d,  per tap: tap_off, tap_sbo, slice_step]
+// Returns the number of ints written, or -1 (bad geometry / buffer too small).  No CUDA call.
+extern "C" int nnd_conv_tct_plan_debug(const int* geom, int mt, int s2, int* out, int cap) {
+  if (!geom || !out || mt < 1 || mt > 4) return -1;
+  ConvGeom g;
+  g.N = geom[0]; g.Di = geom[1]; g.Hi = geom[2]; g.Wi = geom[3]; g.Cin = geom[4];
+  g.Ld = geom[5]; g.Lh = geom[6]; g.Lw = geom[7]; g.sd = geom[8]; g.sh = geom[9]; g.sw = geom[10];
+  g.Do = geom[11]; g.Ho = geom[12]; g.Wo = geom[13];
+  g.omd = geom[14]; g.omh = geom[15]; g.omw = geom[16]; g.ood = geom[17]; g.ooh = geom[18]; g.oow = geom[19];
+  g.T = geom[20];
+  if (g.T < 1 || g.T > NND_MAX_TAPS) return -1;
+  for (int t = 0; t < g.T; ++t) {
+    g.off_d[t] = (signed char)geom[21 + 4 * t]; g.off_h[t] = (signed char)geom[22 + 4 * t]; g.off_w[t] = (signed char)geom[23 + 4 * t];
+    g.tap_w[t] = (unsigned char)geom[24 + 4 * t];
+  }
+  const int rowb = s2 ? 32 : 64;
+  TctHostPlan hp;
+  tct_host_plan(g, mt, rowb, hp);
+  const int need = 4 + hp.tl.n_planes * 10 + g.T * 3;
+  if (cap < need) return -1;
+  int* o = out;
+  *o++ = hp.tl.n_planes; *o++ = hp.a_stage_bytes; *o++ = hp.tl.a_bytes; *o++ = rowb;
+  for (int p = 0; p < hp.tl.n_planes; ++p) {
+    const TctPlane& pl = hp.tl.pl[p];
+    *o++ = pl.pd; *o++ = pl.ph; *o++ = pl.pw; *o++ = pl.cd; *o++ = pl.ch; *o++ = pl.cw; *o++ = pl.base;
+    *o++ = hp.box[p][0]; *o++ = hp.box[p][1]; *o++ = hp.box[p][2];
+  }
+  for (int t = 0; t < g.T; ++t) { *o++ = hp.tl.tap_off[t]; *o++ = hp.tl.tap_sbo[t]; *o++ = hp.tl.slice_step[t]; }
+  return need;
 }

@@ -421,3 +421,34 @@ int nnd_conv_wgrad_tma_s2(const __nv_bfloat16* dy, int Cdy, const __nv_bfloat16*
   if (p.nb == 2) return p.narrow ? launch_ws<2, 1, 32>(maps, a, p.splits, ws, ws_bytes, st) : launch_ws<2, 0, 32>(maps, a, p.splits, ws, ws_bytes, st);
   return p.narrow ? launch_ws<1, 1, 32>(maps, a, p.splits, ws, ws_bytes, st) : launch_ws<1, 0, 32>(maps, a, p.splits, ws, ws_bytes, st);
 }
+
+// Host-only: the plan of a strided launch as flat ints (tests/test_tma_plan_cpu.py replays it in numpy).
+//   out = [narrow, bw, bh, pair, nb, cb, HB, WS, n_groups, ci_tiles, splits, units_per_split, total_units, dxmask,  per group: dz, ty, gtw[3], gtw2[3]]
+extern "C" int nnd_conv_wgrad_tma_s2_plan_debug(const int* geom, int Cdy, int Cx, int* out, int cap) {
+  if (!geom || !out) return -1;
+  ConvGeom g;
+  g.N = geom[0]; g.Di = geom[1]; g.Hi = geom[2]; g.Wi = geom[3]; g.Cin = geom[4];
+  g.Ld = geom[5]; g.Lh = geom[6]; g.Lw = geom[7]; g.sd = geom[8]; g.sh = geom[9]; g.sw = geom[10];
+  g.Do = geom[11]; g.Ho = geom[12]; g.Wo = geom[13];
+  g.omd = geom[14]; g.omh = geom[15]; g.omw = geom[16]; g.ood = geom[17]; g.ooh = geom[18]; g.oow = geom[19];
+  g.T = geom[20];
+  if (g.T < 1 || g.T > NND_MAX_TAPS) return -1;
+  for (int t = 0; t < g.T; ++t) {
+    g.off_d[t] = (signed char)geom[21 + 4 * t]; g.off_h[t] = (signed char)geom[22 + 4 * t]; g.off_w[t] = (signed char)geom[23 + 4 * t];
+    g.tap_w[t] = (unsigned char)geom[24 + 4 * t];
+  }
+  if (!nnd_conv_wgrad_tma_s2_supported(g, Cdy, Cx)) return -1;
+  WsPlan p;
+  ws_plan(g, Cdy, Cx, p);
+  const int need = 14 + p.a.n_groups * 8;
+  if (cap < need) return -1;
+  int* o = out;
+  *o++ = p.narrow; *o++ = p.bw; *o++ = p.bh; *o++ = p.a.pair; *o++ = p.nb; *o++ = p.cb; *o++ = p.a.HB; *o++ = p.a.WS; *o++ = p.a.n_groups;
+  *o++ = p.a.ci_tiles; *o++ = (int)p.splits; *o++ = (int)p.a.units_per_split; *o++ = (int)p.a.total_units; *o++ = p.a.dxmask;
+  for (int n = 0; n < p.a.n_groups; ++n) {
+    *o++ = p.a.gdz[n]; *o++ = p.a.gdy[n];
+    for (int k = 0; k < 3; ++k) *o++ = p.a.gtw[n][k];
+    for (int k = 0; k < 3; ++k) *o++ = p.a.gtw2[n][k];
+  }
+  return need;
+}
